@@ -1,0 +1,46 @@
+# /* **************************************************************************
+#  *                                                                          *
+#  *     (C) Copyright Edward Diener 2011.                                    *
+#  *     (C) Copyright Paul Mensonides 2011.                                  *
+#  *     Distributed under the Boost Software License, Version 1.0. (See      *
+#  *     accompanying file LICENSE_1_0.txt or copy at                         *
+#  *     http://www.boost.org/LICENSE_1_0.txt)                                *
+#  *                                                                          *
+#  ************************************************************************** */
+#
+# /* See http://www.boost.org for most recent version. */
+#
+# ifndef BOOST_PREPROCESSOR_ARRAY_TO_SEQ_HPP
+# define BOOST_PREPROCESSOR_ARRAY_TO_SEQ_HPP
+#
+# include <libint2/boost/preprocessor/cat.hpp>
+# include <libint2/boost/preprocessor/config/config.hpp>
+# include <libint2/boost/preprocessor/array/size.hpp>
+# include <libint2/boost/preprocessor/control/if.hpp>
+# include <libint2/boost/preprocessor/tuple/to_seq.hpp>
+#
+# /* BOOST_PP_ARRAY_TO_SEQ */
+#
+#    define BOOST_PP_ARRAY_TO_SEQ(array) \
+		BOOST_PP_IF \
+			( \
+			BOOST_PP_ARRAY_SIZE(array), \
+			BOOST_PP_ARRAY_TO_SEQ_DO, \
+			BOOST_PP_ARRAY_TO_SEQ_EMPTY \
+			) \
+		(array) \
+/**/
+#    define BOOST_PP_ARRAY_TO_SEQ_EMPTY(array)
+#
+# if BOOST_PP_CONFIG_FLAGS() & BOOST_PP_CONFIG_MSVC()
+#    define BOOST_PP_ARRAY_TO_SEQ_DO(array) BOOST_PP_ARRAY_TO_SEQ_I(BOOST_PP_TUPLE_TO_SEQ, array)
+#    define BOOST_PP_ARRAY_TO_SEQ_I(m, args) BOOST_PP_ARRAY_TO_SEQ_II(m, args)
+#    define BOOST_PP_ARRAY_TO_SEQ_II(m, args) BOOST_PP_CAT(m ## args,)
+# elif BOOST_PP_CONFIG_FLAGS() & BOOST_PP_CONFIG_MWCC()
+#    define BOOST_PP_ARRAY_TO_SEQ_DO(array) BOOST_PP_ARRAY_TO_SEQ_I(array)
+#    define BOOST_PP_ARRAY_TO_SEQ_I(array) BOOST_PP_TUPLE_TO_SEQ ## array
+# else
+#    define BOOST_PP_ARRAY_TO_SEQ_DO(array) BOOST_PP_TUPLE_TO_SEQ array
+# endif
+#
+# endif

@@ -1,0 +1,24 @@
+# /* Copyright (C) 2001
+#  * Housemarque Oy
+#  * http://www.housemarque.com
+#  *
+#  * Distributed under the Boost Software License, Version 1.0. (See
+#  * accompanying file LICENSE_1_0.txt or copy at
+#  * http://www.boost.org/LICENSE_1_0.txt)
+#  */
+#
+# /* Revised by Paul Mensonides (2002) */
+#
+# /* See http://www.boost.org for most recent version. */
+#
+# ifndef BOOST_PREPROCESSOR_COMPARISON_HPP
+# define BOOST_PREPROCESSOR_COMPARISON_HPP
+#
+# include <libint2/boost/preprocessor/comparison/equal.hpp>
+# include <libint2/boost/preprocessor/comparison/greater.hpp>
+# include <libint2/boost/preprocessor/comparison/greater_equal.hpp>
+# include <libint2/boost/preprocessor/comparison/less.hpp>
+# include <libint2/boost/preprocessor/comparison/less_equal.hpp>
+# include <libint2/boost/preprocessor/comparison/not_equal.hpp>
+#
+# endif

@@ -1,0 +1,259 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+
+ctypes front-end to oracle/_ref/liboracle.so = the reference's unmodified
+header-only libint2::Engine / Shell / ShellPair / BasisSet / FmEval_Chebyshev7 /
+eri() (compiled from /root/reference where they lie, see oracle/Makefile) on top
+of the restated CPU kernels of oracle/oracle_kernels.cc.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; the product (libint_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "liboracle.so")
+
+SCREEN_ORIGINAL = 0x0001
+SCREEN_CONSERVATIVE = 0x0010
+SCREEN_SCHWARZ = 0x0100
+SCREEN_SCHWARZ_INF = 0x1000
+
+_lib = None
+
+
+def build(force=False):
+    """Build oracle/_ref/liboracle.so (needs /root/reference; a prebuilt .so is used otherwise)."""
+    ref = os.environ.get("LIBINT_REFERENCE", "/root/reference")
+    if os.path.exists(LIB_PATH) and not force and not os.path.isdir(ref):
+        return LIB_PATH
+    if not os.path.isdir(ref):
+        raise RuntimeError("oracle not built and %s absent" % ref)
+    subprocess.check_call(["make", "-C", HERE, "-j4", "REF=" + ref])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        L.lbo_init.restype = C.c_int
+        L.lbo_boys_cheb7.argtypes = [C.c_double, C.c_int, C.c_int, dp]
+        L.lbo_boys_reference.argtypes = [C.c_double, C.c_int, dp]
+        L.lbo_eri_closed.argtypes = [ip, dp, dp, C.c_int]
+        L.lbo_eri_closed.restype = C.c_double
+        L.lbo_shell_renorm.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
+        L.lbo_solidharmonic_coeff.argtypes = [C.c_int] * 5
+        L.lbo_solidharmonic_coeff.restype = C.c_double
+        L.lbo_compute2.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_int, C.c_double,
+                                   C.c_int, dp, C.c_long]
+        L.lbo_compute2.restype = C.c_long
+        L.lbo_shellpair.argtypes = [ip, ip, ip, dp, dp, dp, C.c_int, C.c_double, C.c_int, dp,
+                                    C.c_int, dp]
+        L.lbo_fock_create.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_int, ip, ip,
+                                      C.c_int]
+        L.lbo_fock_create.restype = C.c_void_p
+        L.lbo_fock_destroy.argtypes = [C.c_void_p]
+        L.lbo_fock_nbf.argtypes = [C.c_void_p]
+        L.lbo_fock_nbf.restype = C.c_long
+        L.lbo_fock_schwarz.argtypes = [C.c_void_p, dp]
+        L.lbo_fock_pairdata.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.c_int]
+        L.lbo_fock_build.argtypes = [C.c_void_p, dp, C.c_double, C.c_int, C.c_long, C.c_long, dp,
+                                     dp]
+        L.lbo_time_quartets.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_long, ip,
+                                        C.c_int, dp]
+        L.lbo_time_quartets.restype = C.c_double
+        L.lbo_basis_load.argtypes = [C.c_char_p, C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, ip, dp,
+                                     dp, dp, ip]
+        L.lbo_init()
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Shells:
+    """Flat shell table: l, pure, nprim (int32), O (n,3), alpha/coeff concatenated."""
+
+    def __init__(self, l, pure, nprim, O, alpha, coeff, raw=True):
+        self.l = np.ascontiguousarray(l, dtype=np.int32)
+        self.pure = np.ascontiguousarray(pure, dtype=np.int32)
+        self.nprim = np.ascontiguousarray(nprim, dtype=np.int32)
+        self.O = np.ascontiguousarray(O, dtype=np.float64).reshape(-1, 3)
+        self.alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        self.coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        self.raw = bool(raw)
+        assert self.alpha.size == self.nprim.sum() == self.coeff.size
+
+    def __len__(self):
+        return len(self.l)
+
+    def offsets(self):
+        return np.concatenate([[0], np.cumsum(self.nprim)]).astype(np.int64)
+
+    def subset(self, idx):
+        off = self.offsets()
+        al = np.concatenate([self.alpha[off[i]:off[i + 1]] for i in idx])
+        co = np.concatenate([self.coeff[off[i]:off[i + 1]] for i in idx])
+        idx = np.asarray(idx)
+        return Shells(self.l[idx], self.pure[idx], self.nprim[idx], self.O[idx], al, co, self.raw)
+
+    def size(self, i):
+        l = int(self.l[i])
+        return 2 * l + 1 if self.pure[i] else (l + 1) * (l + 2) // 2
+
+    def args(self):
+        return (_i(self.l), _i(self.pure), _i(self.nprim), _d(self.O), _d(self.alpha),
+                _d(self.coeff), int(self.raw))
+
+
+def set_unit_normalization(flag):
+    lib().lbo_set_unit_normalization(int(flag))
+
+
+def boys_cheb7(T, mmax, table_mmax=None):
+    out = np.zeros(mmax + 1)
+    lib().lbo_boys_cheb7(float(T), int(mmax), int(table_mmax if table_mmax is not None else mmax),
+                         _d(out))
+    return out
+
+
+def boys_reference(T, mmax):
+    out = np.zeros(mmax + 1)
+    lib().lbo_boys_reference(float(T), int(mmax), _d(out))
+    return out
+
+
+def eri_closed(lmn, alpha, centers, norm_flag=0):
+    lmn = np.ascontiguousarray(lmn, dtype=np.int32).reshape(12)
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64).reshape(4)
+    centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(12)
+    return lib().lbo_eri_closed(_i(lmn), _d(alpha), _d(centers), int(norm_flag))
+
+
+def shell_renorm(l, alpha, coeff):
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+    coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+    oc = np.zeros_like(alpha)
+    om = np.zeros_like(alpha)
+    lib().lbo_shell_renorm(int(l), len(alpha), _d(alpha), _d(coeff), _d(oc), _d(om))
+    return oc, om
+
+
+def solidharmonic_coeff(l, m, lx, ly, lz):
+    return lib().lbo_solidharmonic_coeff(l, m, lx, ly, lz)
+
+
+def compute2(shells, braket=0, screening=SCREEN_ORIGINAL, precision=np.finfo(float).eps,
+             uniform_cart_norm=False):
+    """One shell set through the reference Engine. Returns None if screened out."""
+    n = 1
+    for i in range(len(shells)):
+        n *= shells.size(i)
+    out = np.zeros(n)
+    r = lib().lbo_compute2(int(braket), *shells.args(), int(screening), float(precision),
+                           int(uniform_cart_norm), _d(out), n)
+    if r < 0:
+        raise RuntimeError("lbo_compute2 failed (%d)" % r)
+    if r == 0:
+        return None
+    return out.reshape([shells.size(i) for i in range(len(shells))])
+
+
+def shellpair(shells2, ln_prec, screening=SCREEN_ORIGINAL):
+    cap = int(shells2.nprim[0] * shells2.nprim[1])
+    out = np.zeros((cap, 9))
+    AB = np.zeros(3)
+    n = lib().lbo_shellpair(*shells2.args(), float(ln_prec), int(screening), _d(out), cap, _d(AB))
+    if n < 0:
+        raise RuntimeError("lbo_shellpair failed")
+    return out[:n].copy(), AB
+
+
+class Fock:
+    """Direct Fock build through the reference Engine (hartree-fock++.cc pattern)."""
+
+    def __init__(self, shells, pair_s1, pair_s2, nthreads=1):
+        self.shells = shells
+        p1 = np.ascontiguousarray(pair_s1, dtype=np.int32)
+        p2 = np.ascontiguousarray(pair_s2, dtype=np.int32)
+        self.h = lib().lbo_fock_create(len(shells), *shells.args(), len(p1), _i(p1), _i(p2),
+                                       int(nthreads))
+        self.nbf = lib().lbo_fock_nbf(self.h)
+        self.nshell = len(shells)
+
+    def schwarz(self):
+        K = np.zeros((self.nshell, self.nshell))
+        lib().lbo_fock_schwarz(self.h, _d(K))
+        return K
+
+    def pairdata(self, s1, s2):
+        cap = int(self.shells.nprim[s1] * self.shells.nprim[s2])
+        out = np.zeros((cap, 9))
+        n = lib().lbo_fock_pairdata(self.h, int(s1), int(s2), _d(out), cap)
+        if n < 0:
+            raise KeyError((s1, s2))
+        return out[:n].copy()
+
+    def build(self, D, precision, use_schwarz=True, task_stride=1, task_offset=0):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        G = np.zeros((self.nbf, self.nbf))
+        stats = np.zeros(3)
+        lib().lbo_fock_build(self.h, _d(D), float(precision), int(use_schwarz), int(task_stride),
+                             int(task_offset), _d(G), _d(stats))
+        return G, {"nints": stats[0], "nquartets": stats[1], "seconds": stats[2]}
+
+    def close(self):
+        if self.h:
+            lib().lbo_fock_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def time_quartets(shells, quartets, nthreads=1):
+    q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
+    s = C.c_double(0)
+    t = lib().lbo_time_quartets(len(shells), *shells.args(), len(q), _i(q), int(nthreads),
+                                C.byref(s))
+    return t, s.value
+
+
+def basis_load(name, Z, xyz_bohr, data_path):
+    """Reference BasisSet(name, atoms); data_path must contain basis/<name>.g94."""
+    os.environ["LIBINT_DATA_PATH"] = data_path
+    Z = np.ascontiguousarray(Z, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz_bohr, dtype=np.float64)
+    npt = C.c_int(0)
+    z = np.zeros(1, dtype=np.int32)
+    zd = np.zeros(3)
+    ns = lib().lbo_basis_load(name.encode(), len(Z), _i(Z), _d(xyz), 0, 0, _i(z), _i(z), _i(z),
+                              _d(zd), _d(zd), _d(zd), C.byref(npt))
+    if ns < 0:
+        raise RuntimeError("basis load failed")
+    l = np.zeros(ns, dtype=np.int32)
+    pure = np.zeros(ns, dtype=np.int32)
+    nprim = np.zeros(ns, dtype=np.int32)
+    O = np.zeros((ns, 3))
+    alpha = np.zeros(npt.value)
+    coeff = np.zeros(npt.value)
+    lib().lbo_basis_load(name.encode(), len(Z), _i(Z), _d(xyz), ns, npt.value, _i(l), _i(pure),
+                         _i(nprim), _d(O), _d(alpha), _d(coeff), C.byref(npt))
+    return Shells(l, pure, nprim, O, alpha, coeff, raw=False)
