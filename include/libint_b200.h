@@ -1,0 +1,139 @@
+/* libint_b200.h -- C ABI of the B200 (sm_100a) two-electron Coulomb integral + direct Fock path.
+ *
+ * Drop-in boundary. In the reference (evaleev/libint @ 7a1a9d8) the hot path sits behind
+ *   (1) the generated C interface   Libint_t + libint2_build_eri[la][lb][lc][ld](Libint_t*)
+ *       (src/bin/libint/iface.cc:114-185, used at include/libint2/engine.impl.h:623-635,1898-1899)
+ *   (2) the C++ API                 libint2::Engine::compute2<coulomb, xx_xx|xs_xx, 0>
+ *       (include/libint2/engine.h:787-791, engine.impl.h:1151-2113)
+ *   (3) its consumer                compute_2body_fock (tests/hartree-fock/hartree-fock++.cc:1574-1772)
+ * Those interfaces are one-quartet-at-a-time.  This library keeps their *data contracts*
+ * (Shell normalization, ShellPair primitive screening, Cartesian / solid-harmonic orderings,
+ * row-major n1*n2*n3*n4 result layout, G = J - K/2 digestion convention) and exposes the
+ * batched entry points a binding needs; INTEGRATION.md shows the Engine-side glue.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, error codes (0 = success, negative = error; no exceptions
+ *     cross this boundary).  lb200_last_error() returns a message for the calling context.
+ *   - every "on_device" flag says whether the corresponding buffer is device memory of the
+ *     context's GPU (e.g. a torch CUDA tensor) or host memory.
+ *   - shells carry normalization-embedded coefficients, i.e. what libint2::Shell::contr[0].coeff
+ *     holds after Shell::renorm() (include/libint2/shell.h:958-999); lb200_shell_renorm does that.
+ *   - no CPU fallback: every compute entry point fails with LB200_ERR_CUDA if no GPU is usable.
+ */
+#ifndef LIBINT_B200_H
+#define LIBINT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB200_OK 0
+#define LB200_ERR_INVALID (-1)     /* bad argument / unsupported class                         */
+#define LB200_ERR_CUDA (-2)        /* CUDA runtime error (see lb200_last_error)                  */
+#define LB200_ERR_LMAX (-3)        /* angular momentum beyond the built kernels
+                                      (mirrors Engine::lmax_exceeded, engine.h:893-916)         */
+#define LB200_ERR_NOMEM (-4)
+
+/* ScreeningMethod values, identical to include/libint2/shell.h:1041-1059 */
+#define LB200_SCREEN_ORIGINAL 0x0001
+#define LB200_SCREEN_CONSERVATIVE 0x0010
+#define LB200_SCREEN_SCHWARZ 0x0100
+#define LB200_SCREEN_SCHWARZ_INF 0x1000
+
+#define LB200_MAX_AM 4             /* s..g per shell (LIBINT2_MAX_AM_eri analogue)              */
+
+typedef struct lb200_context lb200_context;
+typedef struct lb200_basis lb200_basis;
+typedef struct lb200_pairs lb200_pairs;
+typedef struct lb200_fock lb200_fock;
+
+/* ---- library / context life cycle: replaces libint2::initialize()/finalize()
+ *      (include/libint2/initialize.h:76-136) and Engine construction (engine.h:503-526). */
+int lb200_version(void);
+int lb200_device_count(void);
+int lb200_context_create(int device, lb200_context** out);
+int lb200_context_destroy(lb200_context* ctx);
+const char* lb200_last_error(const lb200_context* ctx);
+/* use an externally owned CUDA stream (cudaStream_t cast to void*), e.g. torch's current stream */
+int lb200_context_set_stream(lb200_context* ctx, void* cuda_stream);
+int lb200_context_synchronize(lb200_context* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long lb200_context_launch_count(const lb200_context* ctx);
+
+/* ---- Shell normalization: Shell::renorm(), shell.h:958-999. coeff is updated in place;
+ *      max_ln_coeff (shell.h:1001-1011) is optional. */
+int lb200_shell_renorm(int l, int nprim, const double* alpha, double* coeff,
+                       int enforce_unit_normalization, double* max_ln_coeff);
+
+/* ---- basis = std::vector<libint2::Shell> flattened (include/libint2/basis.h.in, shell.h:720):
+ *      l[nshell], pure[nshell], nprim[nshell], origin[3*nshell], then alpha/coeff concatenated
+ *      (sum nprim entries); one contraction per shell, as Engine::compute2 requires
+ *      (engine.impl.h:1167-1171). */
+int lb200_basis_create(lb200_context* ctx, int nshell, const int* l, const int* pure,
+                       const int* nprim, const double* origin, const double* alpha,
+                       const double* coeff, lb200_basis** out);
+/* the unit shell of Shell::unit() (shell.h:906-909,949-953): bra2 of the 3-centre integrals */
+int lb200_basis_create_unit(lb200_context* ctx, lb200_basis** out);
+int lb200_basis_destroy(lb200_basis* bs);
+int lb200_basis_nbf(const lb200_basis* bs);
+int lb200_basis_nshell(const lb200_basis* bs);
+/* first basis function of every shell: BasisSet::shell2bf() */
+int lb200_basis_shell2bf(const lb200_basis* bs, int* out);
+
+/* ---- shell-pair data: ShellPair::init (shell.h:1138-1328), built once and kept on the GPU.
+ *      All pairs of one call must belong to one class (l(s1) >= l(s2), same l's and purity).
+ *      screening: ORIGINAL / CONSERVATIVE use ln_prec as in shell.h:1162-1232;
+ *      SCHWARZ / SCHWARZ_INF need prim_schwarz (one factor per primitive pair, ordered
+ *      [pair][p1][p2], = schwarz_factor_evaluator of hartree-fock++.cc:1390-1412) or NULL to
+ *      have the library compute them on the GPU. */
+int lb200_pairs_create(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* bs2,
+                       int npair, const int* s1, const int* s2, int screening, double ln_prec,
+                       const double* prim_schwarz, lb200_pairs** out);
+int lb200_pairs_destroy(lb200_pairs* p);
+/* info[0..5] = la, lb, npair, total primitive pairs kept, pure_a, pure_b */
+int lb200_pairs_info(const lb200_pairs* p, long long* info);
+/* copies the primitive-pair records of pair i: 9 doubles each
+ * {P[3], K, one_over_gamma, nonsph_screen_fac, ln_scr, p1, p2} (PrimPairData, shell.h:1084-1092);
+ * returns the count */
+int lb200_pairs_get(const lb200_pairs* p, int i, double* out, int cap);
+
+/* ---- batched Engine::compute2<coulomb, *, 0>: one shell set per task.
+ *      tasks = ntasks x {bra pair index, ket pair index}.  Output: ntasks blocks of
+ *      n_a*n_b*n_c*n_d doubles, row-major in the order (bra.first, bra.second, ket.first,
+ *      ket.second); Cartesian (`pure_out` = 0) or, with `pure_out` = 1, transformed for the
+ *      shells flagged pure (engine.impl.h:1965-1985).  A task whose primitives are all
+ *      screened out (results()[0] == nullptr in the reference, engine.impl.h:1781-1784)
+ *      yields zeros.  precision <= 0 disables primitive screening (Engine::set_precision). */
+int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
+                    long long ntasks, const int* tasks, int tasks_on_device, int screening,
+                    double precision, int pure_out, double* out, int out_on_device);
+/* doubles per task written by lb200_eri_batch */
+long long lb200_eri_block_size(const lb200_pairs* bra, const lb200_pairs* ket, int pure_out);
+
+/* ---- direct Fock build: compute_2body_fock (hartree-fock++.cc:1574-1772).
+ *      pairs (s1 >= s2) = the significant shell-pair list obs_shellpair_list
+ *      (hartree-fock++.cc:1305-1381); lb200_significant_pairs computes it.
+ *      create() evaluates the Schwarz matrix (hartree-fock++.cc:1230-1298) and the
+ *      SchwarzInf primitive-pair data (:1383-1431) on the GPU. */
+int lb200_significant_pairs(const lb200_basis* bs, double threshold, int* s1, int* s2,
+                            long long cap, long long* count);
+int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npair, const int* s1,
+                      const int* s2, lb200_fock** out);
+int lb200_fock_destroy(lb200_fock* f);
+int lb200_fock_schwarz(const lb200_fock* f, double* K /* nshell*nshell, host */);
+/* G = 1/2 (g + g^T), g accumulated as in hartree-fock++.cc:1721-1743 from density D (nbf x nbf,
+ * row-major).  Only the quartets with (task id % nranks) == rank are processed, so that N
+ * processes each produce a partial G to be summed (ncclAllReduce by the caller); pass 0, 1
+ * for the whole build.  stats (optional, 4 doubles): shell quartets computed, kernel
+ * launches, device milliseconds, candidate quartets screened. */
+int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double precision,
+                     int use_schwarz, int rank, int nranks, double* G, int G_on_device,
+                     double* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBINT_B200_H */

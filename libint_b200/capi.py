@@ -1,0 +1,316 @@
+"""ctypes binding of the C ABI declared in include/libint_b200.h.
+
+This is the only way Python reaches the CUDA path; there is no CPU fallback: `load()`
+raises if the shared library is missing, and every compute call raises `Lb200Error` when
+the library reports a failure (no GPU, unsupported class, CUDA error).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "liblibint_b200.so")
+
+OK = 0
+SCREEN_ORIGINAL = 0x0001
+SCREEN_CONSERVATIVE = 0x0010
+SCREEN_SCHWARZ = 0x0100
+SCREEN_SCHWARZ_INF = 0x1000
+MAX_AM = 4
+
+
+class Lb200Error(RuntimeError):
+    pass
+
+
+_lib = None
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); also the list tests check against include/libint_b200.h
+SIGNATURES = {
+    "lb200_version": (C.c_int, []),
+    "lb200_device_count": (C.c_int, []),
+    "lb200_context_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "lb200_context_destroy": (C.c_int, [vp]),
+    "lb200_last_error": (C.c_char_p, [vp]),
+    "lb200_context_set_stream": (C.c_int, [vp, vp]),
+    "lb200_context_synchronize": (C.c_int, [vp]),
+    "lb200_context_launch_count": (C.c_longlong, [vp]),
+    "lb200_shell_renorm": (C.c_int, [C.c_int, C.c_int, dp, dp, C.c_int, dp]),
+    "lb200_basis_create": (C.c_int, [vp, C.c_int, ip, ip, ip, dp, dp, dp, C.POINTER(vp)]),
+    "lb200_basis_create_unit": (C.c_int, [vp, C.POINTER(vp)]),
+    "lb200_basis_destroy": (C.c_int, [vp]),
+    "lb200_basis_nbf": (C.c_int, [vp]),
+    "lb200_basis_nshell": (C.c_int, [vp]),
+    "lb200_basis_shell2bf": (C.c_int, [vp, ip]),
+    "lb200_pairs_create": (C.c_int, [vp, vp, vp, C.c_int, ip, ip, C.c_int, C.c_double, dp,
+                                     C.POINTER(vp)]),
+    "lb200_pairs_destroy": (C.c_int, [vp]),
+    "lb200_pairs_info": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
+    "lb200_pairs_get": (C.c_int, [vp, C.c_int, dp, C.c_int]),
+    "lb200_eri_batch": (C.c_int, [vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_double,
+                                  C.c_int, vp, C.c_int]),
+    "lb200_eri_block_size": (C.c_longlong, [vp, vp, C.c_int]),
+    "lb200_significant_pairs": (C.c_int, [vp, C.c_double, ip, ip, C.c_longlong,
+                                          C.POINTER(C.c_longlong)]),
+    "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
+    "lb200_fock_destroy": (C.c_int, [vp]),
+    "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_fock_build": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp,
+                                   C.c_int, dp]),
+}
+
+
+def load():
+    """Load the CUDA extension; fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Lb200Error(
+                "libint_b200 CUDA extension not built: %s missing "
+                "(run `python -m libint_b200.build`); there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(ip)
+
+
+def _ptr(x):
+    """numpy array -> (pointer, on_device=0); torch CUDA tensor -> (pointer, 1)."""
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data), 0
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr()), 1 if x.is_cuda else 0
+    raise TypeError("expected numpy array or torch tensor")
+
+
+class Context:
+    def __init__(self, device=0):
+        L = load()
+        h = vp()
+        rc = L.lb200_context_create(int(device), C.byref(h))
+        if rc != OK:
+            raise Lb200Error("lb200_context_create(device=%d) failed with %d: no usable CUDA "
+                             "device (this library has no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def check(self, rc, what=""):
+        if rc != OK:
+            msg = load().lb200_last_error(self.h)
+            raise Lb200Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(load().lb200_context_set_stream(self.h, vp(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        self.check(load().lb200_context_synchronize(self.h), "synchronize")
+
+    @property
+    def launch_count(self):
+        return load().lb200_context_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            load().lb200_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shell_renorm(l, alpha, coeff, enforce_unit_normalization=True):
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+    c = np.array(coeff, dtype=np.float64)
+    m = np.zeros_like(c)
+    rc = load().lb200_shell_renorm(int(l), len(alpha), _d(alpha), _d(c),
+                                   int(enforce_unit_normalization), _d(m))
+    if rc != OK:
+        raise Lb200Error("lb200_shell_renorm failed (%d)" % rc)
+    return c, m
+
+
+class Basis:
+    """Flat shell table on the library side (coefficients carry the normalization)."""
+
+    def __init__(self, ctx, l, pure, nprim, origin, alpha, coeff, unit=False):
+        self.ctx = ctx
+        h = vp()
+        if unit:
+            ctx.check(load().lb200_basis_create_unit(ctx.h, C.byref(h)), "basis_create_unit")
+            l, pure, nprim, origin, alpha, coeff = [0], [0], [1], [[0, 0, 0]], [0.0], [1.0]
+        self.l = np.ascontiguousarray(l, dtype=np.int32)
+        self.pure = np.ascontiguousarray(pure, dtype=np.int32)
+        self.nprim = np.ascontiguousarray(nprim, dtype=np.int32)
+        self.origin = np.ascontiguousarray(origin, dtype=np.float64).reshape(-1, 3)
+        self.alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        self.coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        if not unit:
+            ctx.check(load().lb200_basis_create(ctx.h, len(self.l), _i(self.l), _i(self.pure),
+                                                _i(self.nprim), _d(self.origin), _d(self.alpha),
+                                                _d(self.coeff), C.byref(h)), "basis_create")
+        self.h = h
+        self.nshell = len(self.l)
+        self.nbf = load().lb200_basis_nbf(h)
+        s2b = np.zeros(self.nshell, dtype=np.int32)
+        load().lb200_basis_shell2bf(h, _i(s2b))
+        self.shell2bf = s2b
+
+    @classmethod
+    def unit(cls, ctx):
+        return cls(ctx, None, None, None, None, None, None, unit=True)
+
+    def size(self, s):
+        l = int(self.l[s])
+        return 2 * l + 1 if self.pure[s] else (l + 1) * (l + 2) // 2
+
+    def close(self):
+        if self.h:
+            load().lb200_basis_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pairs:
+    """A block of shell pairs of one class, resident on the GPU."""
+
+    def __init__(self, ctx, bs1, bs2, s1, s2, screening=SCREEN_ORIGINAL, ln_prec=-np.inf,
+                 prim_schwarz=None):
+        self.ctx, self.bs1, self.bs2 = ctx, bs1, bs2
+        self.s1 = np.ascontiguousarray(s1, dtype=np.int32)
+        self.s2 = np.ascontiguousarray(s2, dtype=np.int32)
+        if not np.isfinite(ln_prec):
+            ln_prec = -np.finfo(np.float64).max
+        ps = None if prim_schwarz is None else np.ascontiguousarray(prim_schwarz, dtype=np.float64)
+        h = vp()
+        ctx.check(load().lb200_pairs_create(ctx.h, bs1.h, bs2.h, len(self.s1), _i(self.s1),
+                                            _i(self.s2), int(screening), float(ln_prec),
+                                            _d(ps) if ps is not None else None, C.byref(h)),
+                  "pairs_create")
+        self.h = h
+        info = (C.c_longlong * 6)()
+        load().lb200_pairs_info(h, info)
+        self.la, self.lb, self.npair, self.nprimpair, self.pure_a, self.pure_b = [int(x) for x in info]
+
+    def get(self, i):
+        cap = int(self.bs1.nprim[self.s1[i]] * self.bs2.nprim[self.s2[i]])
+        out = np.zeros((cap, 9))
+        n = load().lb200_pairs_get(self.h, int(i), _d(out), cap)
+        if n < 0:
+            raise Lb200Error("pairs_get failed")
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            load().lb200_pairs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eri_block_size(bra, ket, pure_out=False):
+    return int(load().lb200_eri_block_size(bra.h, ket.h, int(pure_out)))
+
+
+def eri_batch(ctx, bra, ket, tasks, out=None, screening=SCREEN_ORIGINAL, precision=0.0,
+              pure_out=False):
+    """Batched Engine::compute2. tasks: (n,2) int32 numpy array or torch int32 CUDA tensor;
+    out: numpy array / torch CUDA tensor of n*block doubles (allocated as numpy if None)."""
+    blk = eri_block_size(bra, ket, pure_out)
+    if isinstance(tasks, np.ndarray):
+        tasks = np.ascontiguousarray(tasks, dtype=np.int32).reshape(-1, 2)
+        n = tasks.shape[0]
+    else:
+        n = tasks.shape[0]
+    if out is None:
+        out = np.empty((n, blk))
+    tp, tdev = _ptr(tasks)
+    op, odev = _ptr(out)
+    ctx.check(load().lb200_eri_batch(ctx.h, bra.h, ket.h, n, tp, tdev, int(screening),
+                                     float(precision), int(pure_out), op, odev), "eri_batch")
+    return out
+
+
+def significant_pairs(bs, threshold=1e-12):
+    cnt = C.c_longlong(0)
+    load().lb200_significant_pairs(bs.h, float(threshold), None, None, 0, C.byref(cnt))
+    s1 = np.zeros(cnt.value, dtype=np.int32)
+    s2 = np.zeros(cnt.value, dtype=np.int32)
+    rc = load().lb200_significant_pairs(bs.h, float(threshold), _i(s1), _i(s2), cnt.value,
+                                        C.byref(cnt))
+    if rc != OK:
+        raise Lb200Error("significant_pairs failed (%d)" % rc)
+    return s1, s2
+
+
+class Fock:
+    """Direct Fock builder (compute_2body_fock of the reference's hartree-fock++ driver)."""
+
+    def __init__(self, ctx, obs, pair_s1=None, pair_s2=None, threshold=1e-12):
+        self.ctx, self.obs = ctx, obs
+        if pair_s1 is None:
+            pair_s1, pair_s2 = significant_pairs(obs, threshold)
+        self.pair_s1 = np.ascontiguousarray(pair_s1, dtype=np.int32)
+        self.pair_s2 = np.ascontiguousarray(pair_s2, dtype=np.int32)
+        h = vp()
+        ctx.check(load().lb200_fock_create(ctx.h, obs.h, len(self.pair_s1), _i(self.pair_s1),
+                                           _i(self.pair_s2), C.byref(h)), "fock_create")
+        self.h = h
+
+    def schwarz(self):
+        K = np.zeros((self.obs.nshell, self.obs.nshell))
+        load().lb200_fock_schwarz(self.h, _d(K))
+        return K
+
+    def build(self, D, precision, use_schwarz=True, rank=0, nranks=1, out=None, stats=False):
+        n = self.obs.nbf
+        if out is None:
+            out = np.empty((n, n))
+        if isinstance(D, np.ndarray):
+            D = np.ascontiguousarray(D, dtype=np.float64)
+        Dp, Ddev = _ptr(D)
+        Gp, Gdev = _ptr(out)
+        st = np.zeros(4)
+        self.ctx.check(load().lb200_fock_build(self.h, Dp, Ddev, float(precision), int(use_schwarz),
+                                               int(rank), int(nranks), Gp, Gdev,
+                                               _d(st) if stats else None), "fock_build")
+        if stats:
+            return out, {"nquartets": st[0], "launches": st[1], "ms": st[2], "candidates": st[3]}
+        return out
+
+    def close(self):
+        if self.h:
+            load().lb200_fock_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,495 @@
+// Direct Fock build on the GPU: the consumer of the ERI path,
+// compute_2body_fock of tests/hartree-fock/hartree-fock++.cc:1574-1772, plus its set-up
+// (Schwarz matrix :1230-1298, SchwarzInf shell-pair data :1383-1431, shell-block norms of
+// D :939-957).  Quartet enumeration is re-designed for the GPU: significant shell pairs are
+// grouped by class and sorted by Schwarz bound; for every (bra class, ket class) a
+// screening kernel compacts the surviving (bra pair, ket pair) tasks of a row chunk into a
+// task list that the fused ERI+digestion kernel of that class consumes without a host
+// round trip.  The set of quartets computed and their per-quartet precision are exactly
+// the reference's (same predicate, same unique-quartet rule).
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <numeric>
+
+#include "internal.h"
+
+namespace lb200 {
+int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
+              long long ntasks, const int2* d_tasks, int screening, double precision,
+              double* d_out);
+}
+
+using namespace lb200;
+
+struct FockClass {
+  int la, lb, pa, pb;
+  lb200_pairs* pairs = nullptr;
+  std::vector<double> schwarz;  // sorted descending, same order as pairs
+};
+
+struct lb200_fock {
+  lb200_context* ctx = nullptr;
+  lb200_basis obs;  // private copy
+  std::vector<double> K;  // Schwarz matrix
+  std::vector<FockClass> classes;
+  // device work space (lazily sized)
+  double* d_D = nullptr;
+  double* d_F = nullptr;
+  double* d_Dnorm = nullptr;
+  double* d_scalar = nullptr;
+  int* d_shell2bf = nullptr;
+  int* d_shellsize = nullptr;
+  int2* d_tasks = nullptr;
+  unsigned* d_count = nullptr;
+  unsigned* d_jmax = nullptr;
+  long long task_cap = 0, jmax_cap = 0;
+};
+
+namespace {
+
+// sqrt(max |(ab|ab)|) over the functions of each pair of a block (pure where flagged):
+// the quantity both Schwarz set-ups of the reference take from Engine results
+// (hartree-fock++.cc:1283-1286 and :1403-1409)
+int diag_schwarz(lb200_context* ctx, const lb200_pairs* P, std::vector<double>& out) {
+  const long long n = P->dev.npair;
+  out.assign(n, 0.0);
+  if (n == 0) return LB200_OK;
+  const int l[4] = {P->dev.la, P->dev.lb, P->dev.la, P->dev.lb};
+  const int pure[4] = {P->dev.pure_a, P->dev.pure_b, P->dev.pure_a, P->dev.pure_b};
+  const bool tform = (pure[0] && l[0] > 0) || (pure[1] && l[1] > 0);
+  const long long ncart = (long long)nc(l[0]) * nc(l[1]) * nc(l[0]) * nc(l[1]);
+  long long npure = 1;
+  for (int x = 0; x < 4; ++x) npure *= pure[x] ? lb200::npure(l[x]) : nc(l[x]);
+  const long long chunk = std::max(1ll, std::min(n, (1ll << 27) / (ncart * 8)));
+  int2* d_tasks = nullptr;
+  double *d_cart = nullptr, *d_pure = nullptr, *d_max = nullptr;
+  int rc = check_cuda(ctx, cudaMalloc(&d_tasks, chunk * sizeof(int2)), "cudaMalloc");
+  if (!rc) rc = check_cuda(ctx, cudaMalloc(&d_cart, chunk * ncart * 8), "cudaMalloc");
+  if (!rc && tform) rc = check_cuda(ctx, cudaMalloc(&d_pure, chunk * npure * 8), "cudaMalloc");
+  if (!rc) rc = check_cuda(ctx, cudaMalloc(&d_max, chunk * 8), "cudaMalloc");
+  std::vector<int2> tasks(chunk);
+  for (long long t0 = 0; t0 < n && !rc; t0 += chunk) {
+    const long long nt = std::min(chunk, n - t0);
+    for (long long i = 0; i < nt; ++i) tasks[i] = make_int2((int)(t0 + i), (int)(t0 + i));
+    cudaMemcpyAsync(d_tasks, tasks.data(), nt * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
+    rc = run_store(ctx, P, P, nt, d_tasks, kScreenOriginal, 0., d_cart);
+    if (rc) break;
+    const double* src = d_cart;
+    long long nblk = ncart;
+    if (tform) {
+      rc = check_cuda(ctx, launch_pure_transform(ctx, d_cart, d_pure, nt, l, pure, ctx->stream),
+                      "pure transform");
+      ++ctx->launches;
+      src = d_pure;
+      nblk = npure;
+    }
+    if (!rc) rc = check_cuda(ctx, launch_block_absmax(src, d_max, nt, nblk, ctx->stream), "absmax");
+    ++ctx->launches;
+    if (!rc)
+      rc = check_cuda(ctx, cudaMemcpyAsync(out.data() + t0, d_max, nt * 8, cudaMemcpyDeviceToHost,
+                                           ctx->stream), "copy");
+    if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "diag_schwarz");
+  }
+  cudaFree(d_tasks); cudaFree(d_cart); cudaFree(d_pure); cudaFree(d_max);
+  for (auto& v : out) v = std::sqrt(v);
+  return rc;
+}
+
+// basis whose shells are the individual primitives of `bs`, coefficient 1
+// (Shell::extract_primitive(p, false), shell.h:927-936)
+void primitive_basis(const lb200_basis& bs, lb200_basis& out) {
+  out.ctx = bs.ctx;
+  out.nshell = (int)bs.alpha.size();
+  out.l.clear(); out.pure.clear(); out.nprim.clear(); out.off.clear(); out.shell2bf.clear();
+  out.O.clear(); out.alpha = bs.alpha; out.coeff.assign(bs.alpha.size(), 1.0);
+  out.max_ln_coeff.assign(bs.alpha.size(), 0.0);
+  int nbf = 0;
+  for (int s = 0; s < bs.nshell; ++s)
+    for (int p = 0; p < bs.nprim[s]; ++p) {
+      out.l.push_back(bs.l[s]);
+      out.pure.push_back(bs.pure[s]);
+      out.nprim.push_back(1);
+      out.off.push_back((int)out.off.size());
+      out.shell2bf.push_back(nbf);
+      nbf += bs.size(s);
+      for (int k = 0; k < 3; ++k) out.O.push_back(bs.O[3 * s + k]);
+    }
+  out.off.push_back((int)out.alpha.size());
+  out.nbf = nbf;
+}
+
+__global__ void shellblock_norm_kernel(const double* __restrict__ D, int nbf, int nshell,
+                                       const int* __restrict__ shell2bf,
+                                       const int* __restrict__ shellsize,
+                                       double* __restrict__ Dnorm) {
+  // compute_shellblock_norm, hartree-fock++.cc:939-957: inf-norm (max |element|) per block
+  const long long n2 = (long long)nshell * nshell;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n2;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int s1 = (int)(g / nshell), s2 = (int)(g % nshell);
+    const int b1 = shell2bf[s1], b2 = shell2bf[s2], n1 = shellsize[s1], n2_ = shellsize[s2];
+    double m = 0.0;
+    for (int i = 0; i < n1; ++i)
+      for (int j = 0; j < n2_; ++j) m = fmax(m, fabs(D[(long long)(b1 + i) * nbf + b2 + j]));
+    Dnorm[g] = m;
+  }
+}
+
+__global__ void absmax_kernel(const double* __restrict__ x, long long n, double* out) {
+  __shared__ double sm[32];
+  double m = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      // values are non-negative: integer compare of the bit patterns orders them
+      atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
+struct ScreenParams {
+  PairBlock bra, ket;
+  int same_class;
+  int row0, nrow;            // bra rows of this chunk
+  const unsigned* jmax;      // per bra row (relative to row0): number of ket candidates
+  const double* Dnorm;
+  int nshell;
+  double fock_precision;
+  int use_schwarz;
+  int rank, nranks;
+  int2* tasks;
+  unsigned* count;
+  unsigned cap;
+};
+
+// unique-quartet rule and Schwarz x density screen, hartree-fock++.cc:1628-1677
+__global__ void screen_kernel(const ScreenParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int wid = threadIdx.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + wid; r < p.nrow; r += gridDim.x * warps_per_block) {
+    const int i = p.row0 + r;
+    const unsigned jm = p.jmax[r];
+    const int s1 = p.bra.shell[2 * i], s2 = p.bra.shell[2 * i + 1];
+    const double Ki = p.bra.schwarz[i];
+    const int gi = p.bra.gidx[i];
+    const double* Dn = p.Dnorm;
+    const int ns = p.nshell;
+    const double D12 = Dn[s1 * ns + s2];
+    for (unsigned j0 = 0; j0 < jm; j0 += 32) {
+      const unsigned j = j0 + lane;
+      bool keep = false;
+      if (j < jm) {
+        const int gj = p.ket.gidx[j];
+        keep = !p.same_class || gi >= gj;
+        if (keep && p.nranks > 1) {
+          const unsigned h = (unsigned)gi * 2654435761u + (unsigned)gj * 40503u;
+          keep = (int)((h >> 8) % (unsigned)p.nranks) == p.rank;
+        }
+        if (keep && p.use_schwarz) {
+          const int s3 = p.ket.shell[2 * j], s4 = p.ket.shell[2 * j + 1];
+          double dn = fmax(D12, Dn[s1 * ns + s3]);
+          dn = fmax(dn, Dn[s2 * ns + s3]);
+          dn = fmax(dn, Dn[s1 * ns + s4]);
+          dn = fmax(dn, Dn[s2 * ns + s4]);
+          dn = fmax(dn, Dn[s3 * ns + s4]);
+          const double Kj = p.ket.schwarz[j];
+          // reference multiplies Dnorm * K(s1,s2) * K(s3,s4) with (s1,s2) the larger pair
+          const double est = gi >= gj ? dn * Ki * Kj : dn * Kj * Ki;
+          keep = !(est < p.fock_precision);
+        }
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+      if (ballot) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(p.count, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+          const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
+          if (pos < p.cap) p.tasks[pos] = make_int2(i, (int)j);
+        }
+      }
+    }
+  }
+}
+
+__global__ void symmetrize_kernel(const double* __restrict__ F, double* __restrict__ G, int n) {
+  // hartree-fock++.cc:1766: GG = 0.5 * (G + G^T)
+  const long long n2 = (long long)n * n;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n2;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(g / n), j = (int)(g % n);
+    G[g] = 0.5 * (F[g] + F[(long long)j * n + i]);
+  }
+}
+
+}  // namespace
+
+namespace lb200 {
+
+int compute_prim_schwarz(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* bs2,
+                         int npair, const int* s1, const int* s2, std::vector<double>& out) {
+  lb200_basis pb1, pb2;
+  primitive_basis(*bs1, pb1);
+  primitive_basis(*bs2, pb2);
+  std::vector<int> q1, q2;
+  for (int i = 0; i < npair; ++i)
+    for (int p1 = 0; p1 < bs1->nprim[s1[i]]; ++p1)
+      for (int p2 = 0; p2 < bs2->nprim[s2[i]]; ++p2) {
+        q1.push_back(bs1->off[s1[i]] + p1);
+        q2.push_back(bs2->off[s2[i]] + p2);
+      }
+  lb200_pairs* P = nullptr;
+  int rc = build_pairs(ctx, &pb1, &pb2, (int)q1.size(), q1.data(), q2.data(), kScreenOriginal,
+                       std::numeric_limits<double>::lowest(), nullptr, nullptr, &P);
+  if (rc) return rc;
+  rc = diag_schwarz(ctx, P, out);
+  lb200_pairs_destroy(P);
+  return rc;
+}
+
+}  // namespace lb200
+
+extern "C" {
+
+int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npair, const int* s1,
+                      const int* s2, lb200_fock** out) {
+  if (!ctx || !obs || !out || npair < 0) return LB200_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  auto* f = new lb200_fock;
+  f->ctx = ctx;
+  f->obs = *obs;
+  const int ns = obs->nshell;
+  f->K.assign((size_t)ns * ns, 0.0);
+  // group by class, first shell = higher AM
+  std::map<std::array<int, 4>, std::pair<std::vector<int>, std::vector<int>>> groups;
+  for (long long i = 0; i < npair; ++i) {
+    int a = s1[i], b = s2[i];
+    if (a < 0 || b < 0 || a >= ns || b >= ns) { delete f; return LB200_ERR_INVALID; }
+    if (obs->l[a] < obs->l[b]) std::swap(a, b);
+    auto& g = groups[{obs->l[a], obs->l[b], obs->pure[a], obs->pure[b]}];
+    g.first.push_back(a);
+    g.second.push_back(b);
+  }
+  const double max_engine_precision = std::numeric_limits<double>::epsilon() / 1e10;  // hf++:64
+  const double ln_max_engine_precision = std::log(max_engine_precision);
+  int rc = LB200_OK;
+  for (auto& kv : groups) {
+    auto& a = kv.second.first;
+    auto& b = kv.second.second;
+    const int n = (int)a.size();
+    // shell-level Schwarz bound, no primitive screening (hartree-fock++.cc:1244-1247)
+    lb200_pairs* all = nullptr;
+    rc = build_pairs(ctx, obs, obs, n, a.data(), b.data(), kScreenOriginal,
+                     std::numeric_limits<double>::lowest(), nullptr, nullptr, &all);
+    std::vector<double> ksh;
+    if (!rc) rc = diag_schwarz(ctx, all, ksh);
+    lb200_pairs_destroy(all);
+    if (rc) break;
+    // sort the class by Schwarz bound, descending (stable for reproducibility)
+    std::vector<int> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ksh[x] > ksh[y]; });
+    FockClass fc;
+    fc.la = kv.first[0]; fc.lb = kv.first[1]; fc.pa = kv.first[2]; fc.pb = kv.first[3];
+    std::vector<int> as(n), bs_(n);
+    fc.schwarz.resize(n);
+    for (int i = 0; i < n; ++i) {
+      as[i] = a[ord[i]]; bs_[i] = b[ord[i]]; fc.schwarz[i] = ksh[ord[i]];
+      f->K[(size_t)as[i] * ns + bs_[i]] = f->K[(size_t)bs_[i] * ns + as[i]] = fc.schwarz[i];
+    }
+    // SchwarzInf shell-pair data (hartree-fock++.cc:1383-1431)
+    rc = build_pairs(ctx, obs, obs, n, as.data(), bs_.data(), kScreenSchwarzInf,
+                     ln_max_engine_precision, nullptr, fc.schwarz.data(), &fc.pairs);
+    if (rc) break;
+    f->classes.push_back(std::move(fc));
+  }
+  if (rc) { lb200_fock_destroy(f); return rc; }
+  // kernel orientation wants bra key >= ket key: keep classes sorted by key
+  std::sort(f->classes.begin(), f->classes.end(), [](const FockClass& x, const FockClass& y) {
+    return order_key(x.la, x.lb) < order_key(y.la, y.lb);
+  });
+  std::vector<int> ssz(ns);
+  for (int s = 0; s < ns; ++s) ssz[s] = obs->size(s);
+  cudaMalloc(&f->d_shell2bf, ns * sizeof(int));
+  cudaMalloc(&f->d_shellsize, ns * sizeof(int));
+  cudaMalloc(&f->d_Dnorm, (size_t)ns * ns * 8);
+  cudaMalloc(&f->d_scalar, 8);
+  cudaMalloc(&f->d_count, 4);
+  cudaMemcpy(f->d_shell2bf, obs->shell2bf.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(f->d_shellsize, ssz.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
+  rc = check_cuda(ctx, cudaGetLastError(), "fock_create");
+  if (rc) { lb200_fock_destroy(f); return rc; }
+  *out = f;
+  return LB200_OK;
+}
+
+int lb200_fock_destroy(lb200_fock* f) {
+  if (!f) return LB200_OK;
+  cudaSetDevice(f->ctx->device);
+  for (auto& c : f->classes) lb200_pairs_destroy(c.pairs);
+  cudaFree(f->d_D); cudaFree(f->d_F); cudaFree(f->d_Dnorm); cudaFree(f->d_scalar);
+  cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize); cudaFree(f->d_tasks); cudaFree(f->d_count);
+  cudaFree(f->d_jmax);
+  delete f;
+  return LB200_OK;
+}
+
+int lb200_fock_schwarz(const lb200_fock* f, double* K) {
+  if (!f || !K) return LB200_ERR_INVALID;
+  std::memcpy(K, f->K.data(), f->K.size() * 8);
+  return LB200_OK;
+}
+
+int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double precision,
+                     int use_schwarz, int rank, int nranks, double* G, int G_on_device,
+                     double* stats) {
+  if (!f || !D || !G || nranks < 1 || rank < 0 || rank >= nranks) return LB200_ERR_INVALID;
+  lb200_context* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int n = f->obs.nbf, ns = f->obs.nshell;
+  const size_t n2 = (size_t)n * n;
+  int rc = LB200_OK;
+  if (!f->d_F) rc = check_cuda(ctx, cudaMalloc(&f->d_F, n2 * 8), "cudaMalloc(F)");
+  if (!rc && !f->d_D) rc = check_cuda(ctx, cudaMalloc(&f->d_D, n2 * 8), "cudaMalloc(D)");
+  if (rc) return rc;
+  const long long launches0 = ctx->launches;
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, st);
+  cudaMemcpyAsync(f->d_D, D, n2 * 8, D_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(f->d_F, 0, n2 * 8, st);
+  cudaMemsetAsync(f->d_scalar, 0, 8, st);
+  shellblock_norm_kernel<<<std::min(1024, (ns * ns + 255) / 256), 256, 0, st>>>(
+      f->d_D, n, ns, f->d_shell2bf, f->d_shellsize, f->d_Dnorm);
+  absmax_kernel<<<std::min(1024, (ns * ns + 255) / 256), 256, 0, st>>>(f->d_Dnorm, (long long)ns * ns,
+                                                                     f->d_scalar);
+  ctx->launches += 2;
+  double Dmax = 0;
+  cudaMemcpyAsync(&Dmax, f->d_scalar, 8, cudaMemcpyDeviceToHost, st);
+  if ((rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock: D norms"))) return rc;
+  const double fock_precision = precision;
+  const double needed_engine_precision = fock_precision / Dmax;  // hartree-fock++.cc:1588
+  // task buffer
+  const long long cap = 1ll << 24;
+  if (f->task_cap < cap) {
+    cudaFree(f->d_tasks);
+    if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks, cap * sizeof(int2)), "cudaMalloc(tasks)")))
+      return rc;
+    f->task_cap = cap;
+  }
+  double nquartets = 0, ncand = 0;
+  std::vector<unsigned> jmax;
+  const size_t ncls = f->classes.size();
+  for (size_t X = 0; X < ncls && !rc; ++X)
+    for (size_t Y = 0; Y <= X && !rc; ++Y) {
+      const FockClass& B = f->classes[X];   // key(B) >= key(Y): kernel orientation
+      const FockClass& Kt = f->classes[Y];
+      const int nb = B.pairs->dev.npair, nk = Kt.pairs->dev.npair;
+      if (nb == 0 || nk == 0) continue;
+      if (!class_supported(B.la, B.lb, Kt.la, Kt.lb))
+        return set_error(ctx, LB200_ERR_LMAX, "no kernel built for a class of this basis");
+      // candidate prefix per bra row from the sorted Schwarz bounds:
+      // K_i * K_j * Dmax >= precision is necessary for survival
+      jmax.assign(nb, (unsigned)nk);
+      if (use_schwarz) {
+        for (int i = 0; i < nb; ++i) {
+          const double thr = fock_precision / (Dmax * B.schwarz[i]) * (1.0 - 1e-12);
+          // first j with schwarz[j] < thr  (descending order)
+          int lo = 0, hi = nk;
+          while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (Kt.schwarz[mid] >= thr) lo = mid + 1; else hi = mid;
+          }
+          jmax[i] = (unsigned)lo;
+        }
+      }
+      if ((long long)nb > f->jmax_cap) {
+        cudaFree(f->d_jmax);
+        if ((rc = check_cuda(ctx, cudaMalloc(&f->d_jmax, (size_t)nb * 4), "cudaMalloc(jmax)"))) break;
+        f->jmax_cap = nb;
+      }
+      cudaMemcpyAsync(f->d_jmax, jmax.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st);
+      int row = 0;
+      while (row < nb && !rc) {
+        long long sum = 0;
+        int r1 = row;
+        while (r1 < nb && (r1 == row || sum + jmax[r1] <= cap)) sum += jmax[r1++];
+        if (sum > cap) return set_error(ctx, LB200_ERR_NOMEM, "task buffer too small for one row");
+        if (sum > 0) {
+          ncand += (double)sum;
+          ScreenParams sp{};
+          sp.bra = B.pairs->dev; sp.ket = Kt.pairs->dev;
+          sp.same_class = (X == Y);
+          sp.row0 = row; sp.nrow = r1 - row;
+          sp.jmax = f->d_jmax + row;
+          sp.Dnorm = f->d_Dnorm; sp.nshell = ns;
+          sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
+          sp.rank = rank; sp.nranks = nranks;
+          sp.tasks = f->d_tasks; sp.count = f->d_count; sp.cap = (unsigned)cap;
+          cudaMemsetAsync(f->d_count, 0, 4, st);
+          const int wpb = 8;
+          const int grid = std::min(ctx->num_sms * 8, (sp.nrow + wpb - 1) / wpb);
+          screen_kernel<<<grid, wpb * 32, 0, st>>>(sp);
+          ++ctx->launches;
+          EriParams p{};
+          p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
+          p.tasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
+          p.boys = ctx->d_boys;
+          p.screening = kScreenSchwarzInf;
+          p.D = f->d_D; p.F = f->d_F; p.nbf = n; p.Dnorm = f->d_Dnorm; p.nshell = ns;
+          p.fock_precision = fock_precision;
+          p.needed_engine_precision = needed_engine_precision;
+          p.ln_needed_engine_precision = std::log(needed_engine_precision);
+          rc = check_cuda(ctx, launch_eri(B.la, B.lb, Kt.la, Kt.lb, p, ctx->d_rows, kModeFock,
+                                          ctx->num_sms, st), "launch fock kernel");
+          ++ctx->launches;
+          if (stats) {  // optional accounting costs a sync per chunk
+            unsigned c = 0;
+            cudaMemcpyAsync(&c, f->d_count, 4, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            nquartets += c;
+          }
+        }
+        row = r1;
+      }
+    }
+  if (rc) return rc;
+  double* d_G = nullptr;
+  if (G_on_device) {
+    symmetrize_kernel<<<std::min(4096ll, (long long)(n2 + 255) / 256), 256, 0, st>>>(f->d_F, G, n);
+  } else {
+    d_G = f->d_D;  // D no longer needed
+    symmetrize_kernel<<<std::min(4096ll, (long long)(n2 + 255) / 256), 256, 0, st>>>(f->d_F, d_G, n);
+    cudaMemcpyAsync(G, d_G, n2 * 8, cudaMemcpyDeviceToHost, st);
+  }
+  ++ctx->launches;
+  cudaEventRecord(ev1, st);
+  rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock build");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (stats) {
+    stats[0] = nquartets;
+    stats[1] = (double)(ctx->launches - launches0);
+    stats[2] = ms;
+    stats[3] = ncand;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Device-side data layout of the Coulomb-ERI path (plain structs, shared by host and device).
+#pragma once
+#include <cstdint>
+
+namespace lb200 {
+
+constexpr int kMaxShellL = 4;         // s..g per shell
+constexpr int kBoysOrder = 7;         // degree of the interpolating polynomial
+constexpr int kBoysNInt = 819;        // intervals on [0,117)
+constexpr double kBoysTmax = 117.0;   // above: asymptotic upward recursion
+constexpr int kBoysTableMmax = 24;    // table rows per interval - 1
+
+// One primitive pair of a shell pair: what ShellPair::PrimPairData holds in the reference
+// (include/libint2/shell.h:1084-1092) plus what Engine::compute2 derives from it per quartet
+// (PA, gamma, c_a*c_b; engine.impl.h:1331-1367,1514-1537), computed once instead.
+struct PrimPair {
+  double P[3];    // (alpha_a A + alpha_b B)/gamma  (shell.h:1186-1194)
+  double PA[3];   // P - A; exactly 0 when b is the unit shell (3-centre bra, engine.impl.h:1515)
+  double Kc;      // sqrt(2) pi^(5/4) exp(-rho |AB|^2)/gamma * c_a * c_b   (shell.h:1241-1243)
+  double gamma;   // alpha_a + alpha_b
+  double oog;     // 1/gamma
+  double ln_scr;  // primitive-pair screening value (shell.h:1162-1165,1214-1232,1288-1290)
+  double nonsph;  // nonsph_screen_fac, ScreeningMethod::Conservative only (shell.h:1196-1212)
+  double pad_;
+};
+static_assert(sizeof(PrimPair) == 96, "PrimPair layout");
+
+// A block of shell pairs of one class (la >= lb, fixed purity), first shell = higher AM.
+struct PairBlock {
+  int npair;
+  int la, lb, pure_a, pure_b;
+  const int* prim_off;     // [npair+1] offsets into prim
+  const PrimPair* prim;    // concatenated primitive pairs (screened)
+  const double* AB;        // [npair][3]  A - B
+  const int* shell;        // [npair][2]  shell indices (first, second)
+  const int* bf;           // [npair][2]  first basis function of each shell
+  const double* schwarz;   // [npair]     sqrt(max|(ab|ab)|)          (Fock build only)
+  const int* gidx;         // [npair]     canonical pair index s1(s1+1)/2+s2 (Fock build only)
+};
+
+enum ScreeningMethod : int {  // values follow shell.h:1041-1059
+  kScreenOriginal = 0x0001,
+  kScreenConservative = 0x0010,
+  kScreenSchwarz = 0x0100,
+  kScreenSchwarzInf = 0x1000
+};
+
+enum EriMode : int { kModeStoreCart = 0, kModeStore = 1, kModeFock = 2 };
+
+struct EriParams {
+  PairBlock bra, ket;        // kernel-internal orientation: bra = "lane side"
+  const int2* tasks;         // (bra pair, ket pair) indices
+  const unsigned* ntasks_dev;  // if non-null, task count is read from device memory
+  unsigned ntasks;
+  int swap_tasks;             // 1: tasks are (ket pair, bra pair) in kernel orientation
+  unsigned* work_counter;    // dynamic scheduling counter (zeroed by host)
+  const double* boys;        // [kBoysNInt][kBoysTableMmax+1][8]
+  // primitive screening (engine.impl.h:1313-1314,1371-1386)
+  int screening;
+  double ln_precision;
+  double precision;
+  // store modes
+  double* out;               // [ntasks][out_stride]
+  long long out_stride;
+  int transpose_out;         // 1: caller's bra is the kernel's ket -> write [cd][ab]
+  // Fock mode (tests/hartree-fock/hartree-fock++.cc:1574-1772)
+  const double* D;
+  double* F;
+  int nbf;
+  const double* Dnorm;       // [nshell][nshell] inf-norms of shell blocks of D
+  int nshell;
+  double fock_precision;
+  double ln_needed_engine_precision;
+  double needed_engine_precision;
+  double deg_scale;          // unused by store modes
+};
+
+}  // namespace lb200
