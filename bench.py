@@ -1,0 +1,408 @@
+#!/usr/bin/env python3
+"""bench.py -- the reference's headline metric on B200 (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W              (ours; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+Workload (config.workload = "eri_class_sweep", BASELINE.json configs[1]): one step = one pass
+over the 22 canonical classes (ss|ss)..(dd|dd) (la>=lb, lc>=ld, la+lb<=lc+ld, l<=2), 10^7 random
+primitive shell quartets per class, every Cartesian integral materialised in HBM.
+`value` = shell quartets per second with tasks and outputs resident in HBM; `e2e` = the same
+call with HOST buffers (tasks from pinned host memory, integrals copied back).  Beside it the
+`fock` object times the direct Fock build that consumes the integrals (configs[2],
+(H2O)_64 / def2-TZVP, Schwarz-screened; at N > 1 the quartets are sharded and the partial G's
+all-reduced over NCCL), which is the "Fock-build s at 1/2/4/8 B200" half of the metric.
+Multi-GPU: the sweep is weak-scaled (each rank processes its own 10^7 quartets per class, no
+collective: quartets are independent); the Fock build is strong-scaled.
+
+The CPU oracle (oracle/) is executed only by the cpu_baseline leg and by --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "eri_shell_quartets_per_s"
+UNIT = "shell quartets/s"
+
+
+def nc(l):
+    return (l + 1) * (l + 2) // 2
+
+
+def sweep_classes(lmax=2):
+    from libint_b200.flops import canonical_classes
+    return canonical_classes(lmax)
+
+
+def class_table(cl, npairs, seed):
+    """4*npairs primitive shells: group g holds the shells of index position g of the class.
+    Distribution: centres U(-2,2)^3 bohr, exponents 10^U(-1,1.5), unit coefficients --
+    T = rho*|PQ|^2 spans the Boys interpolation table and the asymptotic branch."""
+    rng = np.random.default_rng(20240607 + seed)
+    n = 4 * npairs
+    l = np.repeat(np.array(cl, dtype=np.int32), npairs)
+    O = rng.uniform(-2.0, 2.0, (n, 3))
+    al = 10.0 ** rng.uniform(-1.0, 1.5, n)
+    co = np.ones(n)
+    return l, np.zeros(n, dtype=np.int32), np.ones(n, dtype=np.int32), O, al, co
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 8:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1])); pw.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                   "reasons": sorted(reasons), "power_w_max": max(pw), "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference legs (oracle = reference Engine on restated kernels; see oracle/)
+# --------------------------------------------------------------------------------------
+def cpu_sweep(classes, npairs, budget_s, nthreads, check=None):
+    """times the reference Engine (one per thread, round-robin) on a bounded sample of every
+    class; returns the equal-count-mix throughput, per-class rates and the sample text."""
+    from oracle import pyoracle as po
+    from libint_b200.flops import quartet_flops
+    per = {}
+    tot_q, tot_t = 0, 0.0
+    tbudget = budget_s / len(classes)
+    for ci, cl in enumerate(classes):
+        tab = class_table(cl, npairs, ci)
+        sh = po.Shells(*tab, raw=False)
+        rng = np.random.default_rng(ci)
+        # size the sample from the flop model (~1.5 GFLOP/s/thread guess), then time it
+        nq = int(min(2_000_000, max(2000, tbudget * nthreads * 1.0e9 / quartet_flops(*cl))))
+        b = rng.integers(0, npairs, nq)
+        k = rng.integers(0, npairs, nq)
+        q4 = np.stack([b, npairs + b, 2 * npairs + k, 3 * npairs + k], axis=1).astype(np.int32)
+        t, _ = po.time_quartets(sh, q4, nthreads)
+        per["".join(map(str, cl))] = nq / t
+        tot_q += nq
+        tot_t += t
+    # equal count per class, as the GPU step: time for one quartet of each class
+    mix = len(classes) / sum(1.0 / r for r in per.values())
+    return mix, per, "equal-count mix over %d classes, %d quartets timed in %.1f s" % (len(classes), tot_q, tot_t)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ncores = os.cpu_count() or 1
+    classes = sweep_classes()
+    vals = []
+    for _ in range(args.warmup):
+        cpu_sweep(classes, args.npairs, 2.0, ncores)
+    t0 = time.time()
+    for _ in range(args.steps):
+        mix, per, sample = cpu_sweep(classes, args.npairs, args.cpu_seconds, ncores)
+        vals.append(mix)
+    wall = time.time() - t0
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "eri_class_sweep", "classes": len(classes), "lmax": 2,
+                       "quartets_per_class": args.quartets, "contraction": 1},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": sample + " (reference libint2::Engine compiled from its own headers "
+                             "on the restated build_eri kernels; the generated library cannot be built here)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "per_class_quartets_per_s": per}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--quartets", type=int, default=10_000_000, help="quartets per class per step")
+    ap.add_argument("--npairs", type=int, default=4096, help="bra / ket shell pairs per class")
+    ap.add_argument("--chunk", type=int, default=1 << 20, help="quartets per launch")
+    ap.add_argument("--e2e-quartets", type=int, default=1 << 19, help="quartets per class in the host-buffer leg")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-fock", action="store_true")
+    ap.add_argument("--fock-waters", default="4,4,4")
+    ap.add_argument("--fock-basis", default="def2-tzvp")
+    ap.add_argument("--fock-precision", type=float, default=1e-10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    from libint_b200 import capi
+    from libint_b200.flops import quartet_flops
+    from libint_b200.fock import allreduce_sum_, init_distributed
+    rank, world, local = init_distributed()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    ctx = capi.Context(local)
+    stream = torch.cuda.Stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # FP64 roofline denominator, measured here (MEASURED_PEAKS.json carries HBM and bf16 only)
+    fp64_peak = max(capi.fp64_peak_probe(ctx, 4096)[0] for _ in range(3))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    classes = sweep_classes()
+    nq, chunk = args.quartets, min(args.chunk, args.quartets)
+    work = []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    max_blk = 0
+    for ci, cl in enumerate(classes):
+        tab = class_table(cl, args.npairs, ci)
+        bs = capi.Basis(ctx, *tab)
+        i = np.arange(args.npairs, dtype=np.int32)
+        bra = capi.Pairs(ctx, bs, bs, i, args.npairs + i)
+        ket = capi.Pairs(ctx, bs, bs, 2 * args.npairs + i, 3 * args.npairs + i)
+        tasks = torch.randint(0, args.npairs, (nq, 2), dtype=torch.int32, device=dev, generator=gen)
+        blk = capi.eri_block_size(bra, ket)
+        max_blk = max(max_blk, blk)
+        work.append({"cl": cl, "bs": bs, "bra": bra, "ket": ket, "tasks": tasks, "blk": blk,
+                     "flops": quartet_flops(*cl), "tab": tab})
+    out = torch.empty(chunk * max_blk, dtype=torch.float64, device=dev)  # > L2 for every class but the smallest
+    nchunks = (nq + chunk - 1) // chunk
+
+    def sweep_step(events=None):
+        with torch.cuda.stream(stream):
+            for w in work:
+                if events is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                for c in range(nchunks):
+                    t = w["tasks"][c * chunk:(c + 1) * chunk]
+                    capi.eri_batch(ctx, w["bra"], w["ket"], t, out=out)
+                if events is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record(stream)
+                    events.append((e0, e1))
+
+    for _ in range(args.warmup):
+        sweep_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count
+    ev_all = []
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for _ in range(args.steps):
+        ev = []
+        sweep_step(ev)
+        ev_all.append(ev)
+    t_end.record(stream)
+    barrier()
+    launches = ctx.launch_count - l0
+    ms_total = max_over_ranks(t_start.elapsed_time(t_end))
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * nq * len(classes) / (ms_step * 1e-3)
+
+    # per-class table and the roofline of the dominant kernel
+    per = {}
+    for ci, w in enumerate(work):
+        ms = float(np.mean([ev[ci][0].elapsed_time(ev[ci][1]) for ev in ev_all]))
+        qps = nq / (ms * 1e-3)
+        per["".join(map(str, w["cl"]))] = {
+            "ms": ms, "quartets_per_s": qps, "tflops": qps * w["flops"] / 1e12,
+            "fp64_frac": qps * w["flops"] / 1e12 / fp64_peak,
+            "hbm_gbs": qps * (8 * w["blk"] + 8) / 1e9, "hbm_frac": qps * (8 * w["blk"] + 8) / 1e9 / hbm_peak,
+            "flops_per_quartet": w["flops"], "bytes_per_quartet": 8 * w["blk"] + 8}
+    dom = max(per, key=lambda k: per[k]["ms"])
+    d = per[dom]
+    roofline = {"bound": "fp64", "kernel": "eri_class_kernel<%s> (%s|%s)" % (dom, dom[:2], dom[2:]),
+                "achieved": d["tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": d["fp64_frac"],
+                "peak_source": "FP64 FMA probe (lb200_fp64_peak_probe) measured in this run; "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "traffic": None, "launch_ms": d["ms"] / nchunks, "share_of_step": d["ms"] / ms_step,
+                "hbm": {"achieved": d["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": d["hbm_frac"],
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback"}}
+
+    # ---- e2e: host buffers through the C ABI (pinned tasks in, integrals out) ----------
+    ne = min(args.e2e_quartets, nq)
+    host_tasks = [w["tasks"][:ne].cpu().pin_memory() for w in work]
+    host_out = torch.empty(ne * max_blk, dtype=torch.float64).pin_memory()
+    h2d = sum(8 * ne for _ in work)
+    d2h = sum(8 * w["blk"] * ne for w in work)
+
+    def e2e_step():
+        for w, ht in zip(work, host_tasks):
+            capi.eri_batch(ctx, w["bra"], w["ket"], ht.numpy(), out=host_out.numpy()[:ne * w["blk"]].reshape(ne, w["blk"]))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    nrep = max(1, min(args.steps, 3))
+    for _ in range(nrep):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / nrep)
+    e2e = {"value": world * ne * len(classes) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "quartets_per_class": ne,
+           "note": "host-buffer lb200_eri_batch; PCIe-bound by the materialised integrals"}
+
+    # ---- the consumer: direct Fock build (configs[2]) -----------------------------------
+    fock = None
+    if not args.no_fock:
+        try:
+            fock = run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_)
+        except capi.Lb200Error as e:
+            fock = {"error": str(e)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "eri_class_sweep", "classes": len(classes), "lmax": 2,
+                       "quartets_per_class": nq, "contraction": 1, "pairs_per_side": args.npairs,
+                       "launch_quartets": chunk,
+                       "l2_policy": "outputs (%.1f GB per class) exceed L2; pair tables are L2-resident by design"
+                                    % (8 * max_blk * chunk / 1e9)},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "per_class": per, "fock": fock}
+
+    if rank == 0 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        mix, cper, sample = cpu_sweep(classes, args.npairs, args.cpu_seconds, ncores)
+        line["cpu_baseline"] = {"value": mix, "unit": UNIT, "cores": ncores, "kind": "port",
+                                "sample": sample, "per_class_quartets_per_s": cper}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_):
+    import torch
+    from libint_b200 import capi
+    from libint_b200.basis import BasisSet, water_cluster
+    nx, ny, nz = [int(x) for x in args.fock_waters.split(",")]
+    atoms = water_cluster(nx, ny, nz)
+    obs = BasisSet(args.fock_basis, atoms)
+    t0 = time.perf_counter()
+    B = capi.Basis(ctx, *obs.flat())
+    f = capi.Fock(ctx, B)
+    setup_s = time.perf_counter() - t0
+    n = obs.nbf
+    rng = np.random.default_rng(7)
+    C = rng.standard_normal((n, max(1, n // 8))) / np.sqrt(n)
+    D = C @ C.T  # symmetric PSD, like C_occ C_occ^T
+    Dh = torch.from_numpy(D).pin_memory()
+    Dd = Dh.to(dev)
+    G = torch.empty((n, n), dtype=torch.float64, device=dev)
+    Gh = torch.empty((n, n), dtype=torch.float64).pin_memory()
+
+    def build():
+        with torch.cuda.stream(stream):
+            f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
+            allreduce_sum_(G)
+
+    build()  # warm-up
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    build()
+    e1.record(stream)
+    barrier()
+    sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    # end to end from host D to host G
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        Dd.copy_(Dh, non_blocking=True)
+        f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
+        allreduce_sum_(G)
+        Gh.copy_(G, non_blocking=True)
+    barrier()
+    e2e_sec = max_over_ranks(time.perf_counter() - t0)
+    _, st = f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G, stats=True)
+    nquart = st["nquartets"]
+    if world > 1:
+        t = torch.tensor([nquart], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t)
+        nquart = float(t.item())
+    return {"workload": "(H2O)_%d / %s direct Fock (J - K/2), Schwarz x density screened at %g"
+                        % (nx * ny * nz, args.fock_basis, args.fock_precision),
+            "nshell": len(obs), "nbf": n, "significant_pairs": int(len(f.pair_s1)),
+            "shell_quartets": nquart, "seconds": sec, "e2e_seconds": e2e_sec,
+            "quartets_per_s": nquart / sec, "setup_seconds": setup_s, "n_gpus": world,
+            "allreduce": "nccl sum of nbf^2 f64" if world > 1 else None,
+            "checksum": float(Gh.abs().sum().item())}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -62,6 +62,9 @@ int lb200_context_set_stream(lb200_context* ctx, void* cuda_stream);
 int lb200_context_synchronize(lb200_context* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long long lb200_context_launch_count(const lb200_context* ctx);
+/* FP64 FMA throughput of the context's GPU, measured by a register-resident FMA loop
+ * (the denominator of the FP64 roofline; no reference counterpart).  Returns TFLOP/s. */
+int lb200_fp64_peak_probe(lb200_context* ctx, int iters, double* tflops, double* ms);
 
 /* ---- Shell normalization: Shell::renorm(), shell.h:958-999. coeff is updated in place;
  *      max_ln_coeff (shell.h:1001-1011) is optional. */
@@ -110,6 +113,9 @@ int lb200_pairs_get(const lb200_pairs* p, int i, double* out, int cap);
 int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
                     long long ntasks, const int* tasks, int tasks_on_device, int screening,
                     double precision, int pure_out, double* out, int out_on_device);
+/* 1 if a kernel exists for (la lb|lc ld) with la >= lb, lc >= ld (either bra/ket order), else 0:
+ * the analogue of a null libint2_build_eri[la][lb][lc][ld] entry (engine.impl.h:1898). */
+int lb200_eri_class_supported(int la, int lb, int lc, int ld);
 /* doubles per task written by lb200_eri_batch */
 long long lb200_eri_block_size(const lb200_pairs* bra, const lb200_pairs* ket, int pure_out);
 
@@ -124,6 +130,10 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
                       const int* s2, lb200_fock** out);
 int lb200_fock_destroy(lb200_fock* f);
 int lb200_fock_schwarz(const lb200_fock* f, double* K /* nshell*nshell, host */);
+/* rank that owns the quartet (bra pair | ket pair), pairs named by their canonical index
+ * s1*(s1+1)/2 + s2 (s1 >= s2); host-callable copy of the rule the screening kernel applies.
+ * Replaces the reference's thread round-robin s1234 % nthreads (hartree-fock++.cc:1665). */
+int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks);
 /* G = 1/2 (g + g^T), g accumulated as in hartree-fock++.cc:1721-1743 from density D (nbf x nbf,
  * row-major).  Only the quartets with (task id % nranks) == rank are processed, so that N
  * processes each produce a partial G to be summed (ncclAllReduce by the caller); pass 0, 1

@@ -54,11 +54,14 @@ SIGNATURES = {
     "lb200_eri_batch": (C.c_int, [vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_double,
                                   C.c_int, vp, C.c_int]),
     "lb200_eri_block_size": (C.c_longlong, [vp, vp, C.c_int]),
+    "lb200_eri_class_supported": (C.c_int, [C.c_int] * 4),
     "lb200_significant_pairs": (C.c_int, [vp, C.c_double, ip, ip, C.c_longlong,
                                           C.POINTER(C.c_longlong)]),
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_fock_task_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "lb200_fp64_peak_probe": (C.c_int, [vp, C.c_int, dp, dp]),
     "lb200_fock_build": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp,
                                    C.c_int, dp]),
 }
@@ -314,3 +317,23 @@ class Fock:
             self.close()
         except Exception:
             pass
+
+
+def task_owner(bra_pair_index, ket_pair_index, nranks):
+    """Rank owning the quartet (bra pair | ket pair); pairs by canonical index s1(s1+1)/2+s2."""
+    r = load().lb200_fock_task_owner(int(bra_pair_index), int(ket_pair_index), int(nranks))
+    if r < 0:
+        raise Lb200Error("lb200_fock_task_owner: invalid argument")
+    return r
+
+
+def fp64_peak_probe(ctx, iters=4096):
+    """Measured FP64 FMA throughput (TFLOP/s, ms) of the context's GPU."""
+    t = C.c_double(0)
+    ms = C.c_double(0)
+    ctx.check(load().lb200_fp64_peak_probe(ctx.h, int(iters), C.byref(t), C.byref(ms)), "fp64_probe")
+    return t.value, ms.value
+
+
+def eri_class_supported(la, lb, lc, ld):
+    return bool(load().lb200_eri_class_supported(int(la), int(lb), int(lc), int(ld)))

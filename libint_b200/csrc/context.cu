@@ -483,6 +483,12 @@ int lb200_pairs_get(const lb200_pairs* p, int i, double* out, int cap) {
   return e - b;
 }
 
+int lb200_eri_class_supported(int la, int lb, int lc, int ld) {
+  if (la < lb || lc < ld || lb < 0 || ld < 0) return 0;
+  if (order_key(la, lb) < order_key(lc, ld)) return class_supported(lc, ld, la, lb) ? 1 : 0;
+  return class_supported(la, lb, lc, ld) ? 1 : 0;
+}
+
 long long lb200_eri_block_size(const lb200_pairs* bra, const lb200_pairs* ket, int pure_out) {
   if (!bra || !ket) return LB200_ERR_INVALID;
   auto sz = [&](int l, int pure) { return (pure_out && pure) ? npure(l) : nc(l); };

@@ -158,6 +158,15 @@ __global__ void absmax_kernel(const double* __restrict__ x, long long n, double*
   }
 }
 
+// which rank computes the quartet (bra pair gi | ket pair gj): a multiplicative hash of the
+// two canonical pair indices, so that every class and every Schwarz-magnitude range is spread
+// evenly over the ranks (the reference's static round-robin s1234 % nthreads,
+// hartree-fock++.cc:1665, needs a serial counter)
+__host__ __device__ inline int task_owner(int gi, int gj, int nranks) {
+  const unsigned h = (unsigned)gi * 2654435761u + (unsigned)gj * 40503u;
+  return (int)((h >> 8) % (unsigned)nranks);
+}
+
 struct ScreenParams {
   PairBlock bra, ket;
   int same_class;
@@ -193,10 +202,7 @@ __global__ void screen_kernel(const ScreenParams p) {
       if (j < jm) {
         const int gj = p.ket.gidx[j];
         keep = !p.same_class || gi >= gj;
-        if (keep && p.nranks > 1) {
-          const unsigned h = (unsigned)gi * 2654435761u + (unsigned)gj * 40503u;
-          keep = (int)((h >> 8) % (unsigned)p.nranks) == p.rank;
-        }
+        if (keep && p.nranks > 1) keep = task_owner(gi, gj, p.nranks) == p.rank;
         if (keep && p.use_schwarz) {
           const int s3 = p.ket.shell[2 * j], s4 = p.ket.shell[2 * j + 1];
           double dn = fmax(D12, Dn[s1 * ns + s3]);
@@ -344,6 +350,11 @@ int lb200_fock_destroy(lb200_fock* f) {
   cudaFree(f->d_jmax);
   delete f;
   return LB200_OK;
+}
+
+int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks) {
+  if (nranks < 1 || bra_pair_index < 0 || ket_pair_index < 0) return LB200_ERR_INVALID;
+  return nranks == 1 ? 0 : task_owner(bra_pair_index, ket_pair_index, nranks);
 }
 
 int lb200_fock_schwarz(const lb200_fock* f, double* K) {

@@ -122,3 +122,51 @@ cudaError_t launch_block_absmax(const double* in, double* out, long long ntasks,
 }
 
 }  // namespace lb200
+
+// ---------------------------------------------------------------------------------------
+// FP64 FMA throughput probe: 8 independent FMA chains per thread, all in registers.
+// ---------------------------------------------------------------------------------------
+namespace lb200 {
+namespace {
+__global__ void __launch_bounds__(256) fma_probe_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace
+}  // namespace lb200
+
+extern "C" int lb200_fp64_peak_probe(lb200_context* ctx, int iters, double* tflops, double* ms_out) {
+  if (!ctx || iters < 1 || !tflops) return LB200_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  double* d = nullptr;
+  int rc = lb200::check_cuda(ctx, cudaMalloc(&d, 8), "cudaMalloc");
+  if (rc) return rc;
+  const int grid = ctx->num_sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  lb200::fma_probe_kernel<<<grid, block, 0, ctx->stream>>>(d, iters / 8 + 1, 0.999999, 1e-9);  // warm-up
+  cudaEventRecord(e0, ctx->stream);
+  lb200::fma_probe_kernel<<<grid, block, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+  cudaEventRecord(e1, ctx->stream);
+  ctx->launches += 2;
+  rc = lb200::check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "fp64 probe");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = 2.0 * 8 * 16 * (double)iters * grid * block;
+  *tflops = ms > 0 ? flops / (ms * 1e-3) / 1e12 : 0.0;
+  if (ms_out) *ms_out = ms;
+  return rc;
+}

@@ -1,0 +1,83 @@
+"""Direct Fock (J - K/2) builder: the consumer of the ERI path, sharded over GPUs.
+
+Mirrors compute_2body_fock of the reference's direct-SCF driver
+(tests/hartree-fock/hartree-fock++.cc:1574-1772; python spelling
+python/src/libint2/engine.cc:230-277): G(D) = 1/2 (g + g^T) with
+g_12 += D_34 (12|34) deg, g_13 -= 1/4 D_24 (12|34) deg, ... over the unique, Schwarz x density
+screened shell quartets.  The reference runs one Engine per CPU thread with static
+round-robin and sums thread-private G's (:1665,:1753-1755); here every GPU (one process per
+GPU, torch.distributed/NCCL) takes the quartets it owns (hash partition inside the screening
+kernel), accumulates a partial G in its own HBM, and one all-reduce(sum, FP64) over NVLink
+combines them.
+"""
+import os
+
+import numpy as np
+
+from . import capi
+from .basis import BasisSet
+
+
+def dist_env():
+    """(rank, world_size, local_rank) from the torchrun environment."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_distributed(backend=None):
+    """One process per GPU; rendezvous from MASTER_ADDR/MASTER_PORT (torchrun)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def allreduce_sum_(G):
+    """In-place sum over ranks of a partial Fock matrix (torch tensor, FP64)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM)
+    return G
+
+
+class FockBuilder:
+    def __init__(self, obs, ctx=None, device=None, pair_threshold=1e-12, rank=None, nranks=None):
+        r, w, local = dist_env()
+        self.rank = r if rank is None else rank
+        self.nranks = w if nranks is None else nranks
+        if ctx is None:
+            ctx = capi.Context(local if device is None else device)
+        self.ctx = ctx
+        self.obs = obs if isinstance(obs, BasisSet) else BasisSet(shells=list(obs))
+        self.basis = capi.Basis(ctx, *self.obs.flat())
+        self.fock = capi.Fock(ctx, self.basis, threshold=pair_threshold)
+        self.nbf = self.basis.nbf
+
+    def schwarz(self):
+        return self.fock.schwarz()
+
+    def build_partial(self, D, precision, out=None, use_schwarz=True, stats=False):
+        """This rank's share of G (no communication). D/out: numpy or torch CUDA tensors."""
+        return self.fock.build(D, precision, use_schwarz=use_schwarz, rank=self.rank,
+                               nranks=self.nranks, out=out, stats=stats)
+
+    def __call__(self, D, precision=1e-12, use_schwarz=True):
+        """Full G on every rank. With torch CUDA input the result is a torch CUDA tensor and the
+        reduction is NCCL; with numpy input on one rank the result is numpy."""
+        import torch
+        if isinstance(D, np.ndarray) and self.nranks == 1:
+            return self.build_partial(D, precision, use_schwarz=use_schwarz)
+        dev = torch.device("cuda", self.ctx.device)
+        Dt = torch.as_tensor(D, dtype=torch.float64).to(dev)
+        G = torch.empty((self.nbf, self.nbf), dtype=torch.float64, device=dev)
+        self.ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        self.build_partial(Dt, precision, out=G, use_schwarz=use_schwarz)
+        allreduce_sum_(G)
+        return G

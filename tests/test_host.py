@@ -1,0 +1,125 @@
+"""Host-side logic and the C-ABI surface; no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """liblibint_b200.so loads without a GPU and exports what include/libint_b200.h declares."""
+    from libint_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "libint_b200.h")).read()
+    declared = set(re.findall(r"\b(lb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export " + name
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+
+
+def test_no_gpu_fails_loudly():
+    """no CPU fallback: without a device context creation raises (on the GPU box it succeeds)."""
+    from libint_b200 import capi
+    if capi.load().lb200_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(capi.Lb200Error):
+        capi.Context(0)
+
+
+def test_shell_renorm_matches_reference(oracle):
+    """lb200_shell_renorm == Shell::renorm (shell.h:958-999) bit for bit."""
+    from libint_b200 import capi
+    rng = np.random.default_rng(0)
+    for l in range(5):
+        for K in (1, 3, 6):
+            al = rng.uniform(0.05, 50.0, K)
+            co = rng.uniform(-1.0, 1.0, K)
+            c, m = capi.shell_renorm(l, al, co, True)
+            rc, rm = oracle.shell_renorm(l, al, co)
+            np.testing.assert_array_equal(c, rc)
+            np.testing.assert_array_equal(m, rm)
+    c, _ = capi.shell_renorm(2, [1.0], [1.0], True)
+    assert c[0] == pytest.approx(1.64592278064949, abs=1e-14)  # tests/unit/test-core.cc:52-55
+
+
+def test_basisset_sizes():
+    """shell / function counts of the BASELINE.json configurations."""
+    from libint_b200.basis import BasisSet, H2O_XYZ_ANGSTROM, alkane, atoms_from_tuples, water_cluster
+    h2o = atoms_from_tuples(H2O_XYZ_ANGSTROM)
+    bs = BasisSet("cc-pVDZ", h2o)
+    assert (len(bs), bs.nbf, bs.max_nprim, bs.max_l) == (12, 24, 8, 2)
+    assert len(BasisSet("6-31g", h2o)) == 9  # python/tests/test_libint2.py:25
+    w64 = water_cluster(4, 4, 4)
+    assert len(w64) == 192
+    bs = BasisSet("def2-tzvp", w64)
+    assert (len(bs), bs.nbf, bs.max_l) == (1216, 2752, 3)
+    bs = BasisSet("cc-pvtz", water_cluster(2, 2, 1))
+    assert (len(bs), bs.nbf) == (22 * 4, 58 * 4)
+    c40 = alkane(40)
+    assert len(c40) == 122 and sum(a.atomic_number == 6 for a in c40) == 40
+    assert (len(BasisSet("def2-tzvp", c40)), BasisSet("def2-tzvp", c40).nbf) == (768, 1732)
+    df = BasisSet("def2-tzvp-jk", c40)
+    assert (len(df), df.nbf, df.max_l) == (1492, 4476, 4)
+    # minimum interatomic distance is chemically sane
+    xyz = np.array([a.xyz for a in c40])
+    d = np.linalg.norm(xyz[:, None] - xyz[None], axis=-1) + np.eye(len(xyz)) * 9
+    assert d.min() > 1.9  # bohr; C-H = 2.06
+
+
+def test_basisset_matches_reference_reader(oracle):
+    """our G94 semantics == BasisSet(name, atoms) of the reference (needs /root/reference)."""
+    if not os.path.isdir("/root/reference/lib/basis"):
+        pytest.skip("reference tree not present")
+    from libint_b200.basis import BasisSet, H2O_XYZ_ANGSTROM, atoms_from_tuples
+    atoms = atoms_from_tuples(H2O_XYZ_ANGSTROM)
+    for name in ["sto-3g", "6-31g", "6-31g*", "cc-pvdz", "aug-cc-pvdz", "cc-pvtz", "def2-tzvp",
+                 "def2-tzvp-jk"]:
+        bs = BasisSet(name, atoms)
+        ref = oracle.basis_load(name, [a.atomic_number for a in atoms], [a.xyz for a in atoms],
+                                "/root/reference/lib")
+        l, pure, nprim, O, al, co = bs.flat()
+        for x, y in ((l, ref.l), (pure, ref.pure), (nprim, ref.nprim), (O, ref.O), (al, ref.alpha),
+                     (co, ref.coeff)):
+            np.testing.assert_array_equal(x, y)
+
+
+def test_read_dotxyz(tmp_path):
+    from libint_b200.basis import ANGSTROM_TO_BOHR, read_dotxyz
+    p = tmp_path / "h2o.xyz"
+    p.write_text("3\n\nO 0.0 -0.07579 0.0\nH 0.86681 0.60144 0.0\nH -0.86681 0.60144 0.0\n")
+    atoms = read_dotxyz(str(p))
+    assert [a.atomic_number for a in atoms] == [8, 1, 1]
+    assert atoms[1].x == 0.86681 * ANGSTROM_TO_BOHR
+    p.write_text("1\n\nXx 0 0 0\n")
+    with pytest.raises(ValueError):
+        read_dotxyz(str(p))
+
+
+def test_task_owner_partitions_quartets():
+    """every (bra pair, ket pair) quartet has exactly one owner and the shares are even."""
+    from libint_b200 import capi
+    npair = 300
+    for nranks in (1, 2, 4, 8):
+        counts = np.zeros(nranks, dtype=int)
+        for gi in range(npair):
+            for gj in range(gi + 1):
+                r = capi.task_owner(gi, gj, nranks)
+                assert 0 <= r < nranks
+                counts[r] += 1
+        assert counts.sum() == npair * (npair + 1) // 2
+        assert counts.max() <= 1.1 * counts.mean() + 5
+    with pytest.raises(capi.Lb200Error):
+        capi.task_owner(1, 1, 0)
+
+
+def test_engine_argument_errors():
+    """Engine ctor contract (tests/unit/test-core.cc:59-78): unsupported requests raise."""
+    from libint_b200 import engine as E
+    with pytest.raises(E.lmax_exceeded):
+        E.Engine(E.Operator.coulomb, 1, 7, ctx=object())
+    with pytest.raises(NotImplementedError):
+        E.Engine(E.Operator.coulomb, 1, 1, deriv_order=1, ctx=object())
