@@ -1,0 +1,512 @@
+// Row-parallel, register-resident Obara-Saika / Head-Gordon-Pople kernel for one class
+// (LA LB|LC LD).
+//
+// What it replaces: the generated libint2_build_eri[..] kernel (spec: src/bin/libint/dg.cc:
+// 1128-1188) and the per-primitive prerequisite set-up of Engine::compute2
+// (include/libint2/engine.impl.h:1310-1767) for a batch of shell quartets; recurrences as in
+// vrr_11_twoprep_11.h:154-222 (build on A), :305-383 (build on C) and hrr.h:246,:324.
+//
+// Layout.  The pair with the smaller Cartesian footprint is the "row" side (LA LB|: every
+// (e 0| component with e <= LA+LB is one ROW and one lane owns one row of one quartet, so a
+// CTA of THREADS lanes works on THREADS / NEC quartets at a time (NEC = 1 degenerates to a
+// plain thread-per-quartet kernel).  Everything on the other side |LC LD) is unrolled at
+// compile time and lives in the lane's registers:
+//
+//   per surviving primitive quartet
+//     prerequisites                      every lane, registers
+//     Boys F_m(T)*pfac                   lanes m of the quartet -> shared -> all lanes
+//     [row 0|00]^(m), m <= LC+LD         private chain x..xy..yz..z in registers, no exchange
+//     [row 0|f 0]^(m), f = 1..LC+LD      level by level in registers; only the cross term
+//                                        [row-1_d 0|f-1_d 0]^(m+1) comes from another lane,
+//                                        through one shared-memory read per value
+//     accumulate (e0|f0), e>=LA, f>=LC   registers
+//   ket HRR -> (row 0|c d)               registers, per row
+//   transpose through shared memory, bra HRR -> (a b|c d) by lanes over (quartet, cd), registers
+//   store, or cart->pure + J/K digestion (Fock mode)
+//
+// FP64 operands therefore come from registers; shared memory carries ~1.5 doubles per value
+// instead of the ~7 of the all-shared team kernel (eri_kernel.cuh), which the FP64:LDS
+// throughput ratio of the SM (64 DFMA/clk vs 16 doubles/clk) makes the difference between a
+// shared-memory-bound and an FP64-bound kernel.
+#pragma once
+#include "eri_kernel.cuh"
+#include "fock_digest.cuh"
+
+namespace lb200 {
+
+template <int LA, int LB, int LC, int LD>
+struct RR {
+  static_assert(LA >= LB && LC >= LD, "class must be canonical within each pair");
+  static constexpr int EMAX = LA + LB, FMAX = LC + LD, L = EMAX + FMAX;
+  static constexpr int NEC = nc_upto(EMAX);        // rows per quartet
+  static constexpr int NECX = nc_upto(EMAX - 1);   // rows that feed cross terms (e < EMAX)
+  static constexpr int ROW0 = nc_upto(LA - 1), NRT = NEC - ROW0, RTP = NRT | 1;
+  static constexpr int F0 = nc_upto(LC - 1), NFT = nc_upto(FMAX) - F0;
+  static constexpr int NA = nc(LA), NB = nc(LB), NC = nc(LC), ND = nc(LD);
+  static constexpr int NAB = NA * NB, NCD = NC * ND, CS = NCD | 1;
+  // cross-term slots: level f < FMAX, component j, m = 1..FMAX-f
+  static constexpr int xbase(int f) {
+    int s = 0;
+    for (int g = 0; g < f; ++g) s += nc(g) * (FMAX - g);
+    return s;
+  }
+  static constexpr int XSLOTS = xbase(FMAX);
+  static constexpr int xslot(int f, int j, int m) { return xbase(f) + j * (FMAX - f) + (m - 1); }
+  // per-quartet shared-memory region (doubles); the phases alias each other
+  static constexpr int HDR = 8;                       // AB[3], CD[3], flags
+  static constexpr int OFF_F = HDR;                   // Boys values
+  static constexpr int OFF_X = OFF_F + ((L + 2) & ~1);
+  static constexpr int PRIM_DOUBLES = OFF_X + (EMAX > 0 ? XSLOTS * NECX : 0);
+  static constexpr int TB_DOUBLES = HDR + (LB > 0 ? NCD * RTP : 0);
+  // Fock mode: final integrals [NAB][CS] at HDR, then a second buffer used first as the
+  // row->column transpose buffer and afterwards by the cart->pure passes
+  static constexpr int OFF_B2 = HDR + NAB * CS;
+  static constexpr int FOCK_DOUBLES = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);
+  static constexpr int qsize(bool fock) {
+    int s = cmax(PRIM_DOUBLES, TB_DOUBLES);
+    if (fock) s = cmax(s, FOCK_DOUBLES);
+    return (s + 1) & ~1;
+  }
+  static constexpr int threads() {
+    if (NEC <= 32) return 128;
+    if (NEC == 35) return 128;   // 3 quartets, 105 lanes
+    if (NEC == 56) return 128;   // 2 quartets, 112 lanes
+    return 96;                   // NEC = 84: 1 quartet
+  }
+  static constexpr int THREADS = threads();
+  static constexpr int QPC = THREADS / NEC;           // quartets per CTA round
+};
+
+// one level of the register pyramid: [row 0|f 0]^(m), component j, m = 0..FMAX-F
+template <int FMAX, int F>
+struct Lvl {
+  static constexpr int NM = FMAX - F + 1;
+  double v[nc(F) * NM];
+};
+
+struct RowMeta {   // per lane, fixed for the whole kernel
+  int row, e;
+  int rm[3];       // row index of the component with q[d]-1 (0 if q[d] == 0)
+  double q[3];     // x,y,z quantum numbers of the row
+};
+
+template <class K, int F, class P1, class P2>
+__device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p1, const P2& p2,
+                                               const double (&QC)[3], const double (&WQ)[3],
+                                               const double (&koo2e)[4], double roe,
+                                               const double (&ce)[3], double* __restrict__ Xq,
+                                               const RowMeta& rmeta, double* __restrict__ acc) {
+  constexpr int NM = K::FMAX - F + 1;
+  static_for<nc(F)>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    constexpr C3 q = cxyz(F, j);
+    constexpr int d = cdir(q);
+    constexpr int qd = cget(q, d);
+    constexpr int jm1 = cidx(cadd(q, d, -1));
+    static_for<NM>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      double v = QC[d] * p1.v[jm1 * (NM + 1) + m] + WQ[d] * p1.v[jm1 * (NM + 1) + m + 1];
+      if constexpr (qd > 1) {
+        constexpr int jm2 = cidx(cadd(q, d, -2));
+        v += koo2e[qd - 1] * (p2.v[jm2 * (NM + 2) + m] - roe * p2.v[jm2 * (NM + 2) + m + 1]);
+      }
+      if constexpr (K::EMAX > 0)
+        v += ce[d] * Xq[K::xslot(F - 1, jm1, m + 1) * K::NECX + rmeta.rm[d]];
+      out.v[j * NM + m] = v;
+      if constexpr (F < K::FMAX && m >= 1 && K::EMAX > 0) {
+        if (rmeta.row < K::NECX) Xq[K::xslot(F, j, m) * K::NECX + rmeta.row] = v;
+      }
+      if constexpr (m == 0 && F >= K::LCv) acc[nc_upto(F - 1) - K::F0 + j] += v;
+    });
+  });
+}
+
+template <int LA, int LB, int LC, int LD>
+struct RRK : RR<LA, LB, LC, LD> {
+  static constexpr int LCv = LC;
+};
+
+// HRR in registers for a pair (LX >= LY): in = level 0 blocks x in [LX, LX+LY] (nc(x) each),
+// out = nc(LX) * nc(LY) values, index ix * nc(LY) + iy.  V = displacement vector (A-B / C-D).
+template <int LX, int LY, int N0>
+__device__ __forceinline__ void rr_hrr_regs(const double (&in0)[N0], const double (&V)[3],
+                                            double (&out)[nc(LX) * nc(LY)]) {
+  using H = Cls<LX, 0, 0, 0>;  // only for hoff/hsize helpers
+  if constexpr (LY == 0) {
+    static_for<nc(LX)>([&](auto ic) { out[decltype(ic)::value] = in0[decltype(ic)::value]; });
+  } else {
+    constexpr int S1 = H::hsize(LX, LY, 1);
+    double a[S1];
+    // level 1 from level 0
+    static_for<LY>([&](auto xc) {  // x = LX .. LX+LY-1
+      constexpr int x = LX + decltype(xc)::value;
+      static_for<nc(x)>([&](auto ixc) {
+        constexpr int ix = decltype(ixc)::value;
+        static_for<3>([&](auto iyc) {
+          constexpr int iy = decltype(iyc)::value;  // p component: x,y,z <-> d = iy
+          constexpr int d = iy;
+          constexpr int ixp1 = cidx(cadd(cxyz(x, ix), d, +1));
+          constexpr int o = H::hoff(LX, x, 1) + ix * 3 + iy;
+          constexpr int hi = H::hoff(LX, x + 1, 0) + ixp1;
+          constexpr int lo = H::hoff(LX, x, 0) + ix;
+          a[o] = in0[hi] + V[d] * in0[lo];
+        });
+      });
+    });
+    if constexpr (LY == 1) {
+      static_for<nc(LX) * 3>([&](auto ic) { out[decltype(ic)::value] = a[decltype(ic)::value]; });
+    } else {
+      constexpr int S2 = H::hsize(LX, LY, 2);
+      double b[S2];
+      static_for<LY - 1>([&](auto xc) {
+        constexpr int x = LX + decltype(xc)::value;
+        static_for<nc(x)>([&](auto ixc) {
+          constexpr int ix = decltype(ixc)::value;
+          static_for<6>([&](auto iyc) {
+            constexpr int iy = decltype(iyc)::value;
+            constexpr C3 qy = cxyz(2, iy);
+            constexpr int d = cdir(qy);
+            constexpr int iym1 = cidx(cadd(qy, d, -1));
+            constexpr int ixp1 = cidx(cadd(cxyz(x, ix), d, +1));
+            constexpr int o = H::hoff(LX, x, 2) + ix * 6 + iy;
+            constexpr int hi = H::hoff(LX, x + 1, 1) + ixp1 * 3 + iym1;
+            constexpr int lo = H::hoff(LX, x, 1) + ix * 3 + iym1;
+            b[o] = a[hi] + V[d] * a[lo];
+          });
+        });
+      });
+      if constexpr (LY == 2) {
+        static_for<nc(LX) * 6>([&](auto ic) { out[decltype(ic)::value] = b[decltype(ic)::value]; });
+      } else {
+        static_assert(LY == 3, "HRR in registers is written for LY <= 3");
+        static_for<nc(LX)>([&](auto ixc) {
+          constexpr int ix = decltype(ixc)::value;
+          constexpr int x = LX;
+          static_for<10>([&](auto iyc) {
+            constexpr int iy = decltype(iyc)::value;
+            constexpr C3 qy = cxyz(3, iy);
+            constexpr int d = cdir(qy);
+            constexpr int iym1 = cidx(cadd(qy, d, -1));
+            constexpr int ixp1 = cidx(cadd(cxyz(x, ix), d, +1));
+            constexpr int hi = H::hoff(LX, x + 1, 2) + ixp1 * 6 + iym1;
+            constexpr int lo = H::hoff(LX, x, 2) + ix * 6 + iym1;
+            out[ix * 10 + iy] = b[hi] + V[d] * b[lo];
+          });
+        });
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double sel3(int d, double x, double y, double z) {
+  return d == 0 ? x : (d == 1 ? y : z);
+}
+
+template <int LA, int LB, int LC, int LD, int MODE>
+__global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS)
+eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
+  using K = RRK<LA, LB, LC, LD>;
+  constexpr bool FOCK = (MODE == kModeFock);
+  constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
+  constexpr int QPC = K::QPC, QSIZE = K::qsize(FOCK), THREADS = K::THREADS;
+  static_assert(FMAX <= 4, "register pyramid is sized for LC+LD <= 4");
+
+  extern __shared__ double smem[];
+  __shared__ int s_maxit[3];  // rotating: slot r%3 is reduced in round r, slot (r+1)%3 re-zeroed
+
+  const int tid = threadIdx.x;
+  const int q = tid / NEC;            // quartet slot of this lane
+  const bool lane_on = q < QPC;       // leftover lanes only take part in barriers and phase 2
+  RowMeta rmeta;
+  // leftover lanes get a row index past every "row < NECX" / "row >= ROW0" guarded write
+  // (NEC <= 84 < kMaxRows: still a valid RowInfo index)
+  rmeta.row = lane_on ? tid - q * NEC : NEC;
+  {
+    const RowInfo ri = rows[rmeta.row];
+    rmeta.e = ri.e;
+    for (int d = 0; d < 3; ++d) {
+      rmeta.rm[d] = ri.rm[d];
+      rmeta.q[d] = (double)ri.q[d];
+    }
+  }
+  // private chain of build steps for [row 0|00]: slots EMAX-e .. EMAX-1 are real steps
+  int cdir_[EMAX > 0 ? EMAX : 1];
+  double ccnt_[EMAX > 0 ? EMAX : 1];
+  if constexpr (EMAX > 0) {
+    const int qx = (int)rmeta.q[0], qy = (int)rmeta.q[1];
+    static_for<EMAX>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      const int s = k - (EMAX - rmeta.e);  // index of the real step, < 0: no-op
+      int d = -1, c = 0;
+      if (s >= 0) {
+        if (s < qx) { d = 0; c = s; }
+        else if (s < qx + qy) { d = 1; c = s - qx; }
+        else { d = 2; c = s - qx - qy; }
+      }
+      cdir_[k] = d;
+      ccnt_[k] = (double)c;
+    });
+  }
+  double* const Q = smem + (size_t)(lane_on ? q : 0) * QSIZE;  // this lane's quartet region
+
+  const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
+  if (tid < 3) s_maxit[tid] = 0;
+  __syncthreads();
+  int round = 0;
+  for (unsigned base = blockIdx.x * QPC; base < ntasks; base += gridDim.x * QPC) {
+    const unsigned task = base + q;
+    const bool valid = lane_on && task < ntasks;
+    int ib = 0, ik = 0, pb0 = 0, nb = 0, pk0 = 0, nk = 0;
+    if (valid) {
+      const int2 tk = p.tasks[task];
+      ib = p.swap_tasks ? tk.y : tk.x;
+      ik = p.swap_tasks ? tk.x : tk.y;
+      pb0 = p.bra.prim_off[ib];
+      nb = p.bra.prim_off[ib + 1] - pb0;
+      pk0 = p.ket.prim_off[ik];
+      nk = p.ket.prim_off[ik + 1] - pk0;
+    }
+    const int nit = nb * nk;
+    // slot (round+1)%3 was last read in round-2, i.e. before the barrier of round-1
+    if (tid == 0) s_maxit[(round + 1) % 3] = 0;
+    if (valid && rmeta.row == 0 && nit > 0) atomicMax(&s_maxit[round % 3], nit);
+
+    // ---- per-quartet screening precision ----------------------------------------------
+    double ln_prec = p.ln_precision, prec = p.precision, deg = 1.0;
+    if constexpr (FOCK) {
+      if (valid) {  // hartree-fock++.cc:1667-1695
+        const int s1 = p.bra.shell[2 * ib], s2 = p.bra.shell[2 * ib + 1];
+        const int s3 = p.ket.shell[2 * ik], s4 = p.ket.shell[2 * ik + 1];
+        const double* Dn = p.Dnorm;
+        const int ns = p.nshell;
+        double dn = fmax(Dn[s1 * ns + s2], Dn[s1 * ns + s3]);
+        dn = fmax(dn, Dn[s2 * ns + s3]);
+        dn = fmax(dn, Dn[s1 * ns + s4]);
+        dn = fmax(dn, Dn[s2 * ns + s4]);
+        dn = fmax(dn, Dn[s3 * ns + s4]);
+        if (dn != 0.0) {
+          prec = p.fock_precision / dn;
+          ln_prec = log(prec);
+        } else {
+          prec = p.needed_engine_precision;
+          ln_prec = p.ln_needed_engine_precision;
+        }
+        const double d12 = (s1 == s2) ? 1.0 : 2.0, d34 = (s3 == s4) ? 1.0 : 2.0;
+        const bool same = (s1 == s3 && s2 == s4) || (s1 == s4 && s2 == s3);
+        deg = d12 * d34 * (same ? 1.0 : 2.0);
+      }
+    }
+    double CD[3] = {0, 0, 0};
+    if (valid) {
+      CD[0] = p.ket.AB[3 * ik]; CD[1] = p.ket.AB[3 * ik + 1]; CD[2] = p.ket.AB[3 * ik + 2];
+    }
+    const double npbraket = (double)nb * (double)nk;
+    double acc[K::NFT];
+    static_for<K::NFT>([&](auto ic) { acc[decltype(ic)::value] = 0.0; });
+    int nsurv = 0;
+    __syncthreads();   // also separates the previous round's phase 2 from this round's writes
+    const int maxit = s_maxit[round % 3];
+    ++round;
+
+    for (int it = 0; it < maxit; ++it) {
+      // ---- prerequisites (engine.impl.h:1331-1367,1389-1392,1602-1641) ----------------
+      bool on = valid && it < nit;
+      PrimPair bp, kp;
+      double pfac = 0.0, Targ = 0.0, rho = 0.0, oogpq = 0.0;
+      if (on) {
+        const int ipb = it / nk;
+        const int ipk = it - ipb * nk;
+        bp = p.bra.prim[pb0 + ipb];
+        kp = p.ket.prim[pk0 + ipk];
+        on = bp.ln_scr + kp.ln_scr > ln_prec;  // engine.impl.h:1313-1314
+      }
+      if (on) {
+        const double PQx = bp.P[0] - kp.P[0], PQy = bp.P[1] - kp.P[1], PQz = bp.P[2] - kp.P[2];
+        const double PQ2 = PQx * PQx + PQy * PQy + PQz * PQz;
+        const double gpq = bp.gamma + kp.gamma;
+        oogpq = 1.0 / gpq;
+        pfac = bp.Kc * kp.Kc * sqrt(gpq) * oogpq;
+        if (p.screening & (kScreenOriginal | kScreenConservative)) {  // engine.impl.h:1371-1386
+          double est = fabs(pfac);
+          if (p.screening == kScreenConservative)
+            est *= fmax(1.0, bp.nonsph * kp.nonsph) * npbraket;
+          if (est < prec) on = false;
+        }
+        rho = bp.gamma * kp.gamma * oogpq;
+        Targ = PQ2 * rho;
+      }
+      double PA[3], WP[3], QC[3], WQ[3], oo2z = 0, roz = 0, koo2e[4], roe = 0, ce[3];
+      if (on) {
+        ++nsurv;
+        const double gp = oogpq * bp.gamma, gq = oogpq * kp.gamma;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double W = gp * bp.P[d] + gq * kp.P[d];
+          WP[d] = W - bp.P[d];
+          WQ[d] = W - kp.P[d];
+          PA[d] = bp.PA[d];
+          QC[d] = kp.PA[d];
+        }
+        oo2z = 0.5 * bp.oog;
+        roz = rho * bp.oog;
+        const double oo2e = 0.5 * kp.oog;
+        koo2e[0] = 0.0; koo2e[1] = oo2e; koo2e[2] = 2.0 * oo2e; koo2e[3] = 3.0 * oo2e;
+        roe = rho * kp.oog;
+        const double oo2ze = 0.5 * oogpq;
+        ce[0] = rmeta.q[0] * oo2ze; ce[1] = rmeta.q[1] * oo2ze; ce[2] = rmeta.q[2] * oo2ze;
+      } else {
+        pfac = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) PA[d] = WP[d] = QC[d] = WQ[d] = ce[d] = 0.0;
+        koo2e[0] = koo2e[1] = koo2e[2] = koo2e[3] = 0.0;
+      }
+
+      // ---- Boys: lanes m of the quartet, then broadcast through shared memory ----------
+      double F[L + 1];
+      if constexpr (NEC == 1) {
+        static_for<L + 1>([&](auto mc) {
+          constexpr int m = decltype(mc)::value;
+          F[m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
+        });
+      } else {
+        if (lane_on)
+          for (int m = rmeta.row; m <= L; m += NEC)
+            Q[K::OFF_F + m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
+        __syncthreads();
+        static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] = Q[K::OFF_F + decltype(mc)::value]; });
+      }
+
+      // ---- [row 0|00]^(m): private chain (vrr_11_twoprep_11.h:154-222) ------------------
+      Lvl<FMAX, 0> l0;
+      if constexpr (EMAX == 0) {
+        static_for<FMAX + 1>([&](auto mc) { l0.v[decltype(mc)::value] = F[decltype(mc)::value]; });
+      } else {
+        double cur[L + 1], prv[L + 1];
+        static_for<L + 1>([&](auto mc) {
+          cur[decltype(mc)::value] = F[decltype(mc)::value];
+          prv[decltype(mc)::value] = 0.0;
+        });
+        static_for<EMAX>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          const int d = cdir_[k];
+          const double pa = d < 0 ? 1.0 : sel3(d, PA[0], PA[1], PA[2]);
+          const double wp = d < 0 ? 0.0 : sel3(d, WP[0], WP[1], WP[2]);
+          const double c = ccnt_[k] * oo2z;
+          static_for<L - k>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            const double nv = pa * cur[m] + wp * cur[m + 1] + c * (prv[m] - roz * prv[m + 1]);
+            prv[m] = cur[m];
+            cur[m] = nv;
+          });
+        });
+        static_for<FMAX + 1>([&](auto mc) { l0.v[decltype(mc)::value] = cur[decltype(mc)::value]; });
+        // level-0 cross values
+        if (lane_on && rmeta.row < NECX)
+          static_for<FMAX>([&](auto mc) {
+            constexpr int m = decltype(mc)::value + 1;
+            Q[K::OFF_X + K::xslot(0, 0, m) * NECX + rmeta.row] = l0.v[m];
+          });
+      }
+      if constexpr (LC == 0) acc[0] += l0.v[0];
+
+      // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -------------------
+      double* Xq = Q + K::OFF_X;
+      if constexpr (FMAX >= 1) {
+        if constexpr (EMAX > 0) __syncthreads();
+        Lvl<FMAX, 1> l1;
+        rr_build_level<K, 1>(l1, l0, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+        if constexpr (FMAX >= 2) {
+          if constexpr (EMAX > 0) __syncthreads();
+          Lvl<FMAX, 2> l2;
+          rr_build_level<K, 2>(l2, l1, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+          if constexpr (FMAX >= 3) {
+            if constexpr (EMAX > 0) __syncthreads();
+            Lvl<FMAX, 3> l3;
+            rr_build_level<K, 3>(l3, l2, l1, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+            if constexpr (FMAX >= 4) {
+              if constexpr (EMAX > 0) __syncthreads();
+              Lvl<FMAX, 4> l4;
+              rr_build_level<K, 4>(l4, l3, l2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+            }
+          }
+        }
+      }
+      // the next iteration's first shared write (Boys values / level-0 cross values) must not
+      // overtake this iteration's last cross-term reads
+      if constexpr (EMAX > 0) __syncthreads();
+    }
+
+    // ---- ket HRR in registers: (row 0|c d) from (row 0|f 0), hrr.h:324 -------------------
+    double H[K::NCD];
+    rr_hrr_regs<LC, LD>(acc, CD, H);
+    const bool screened_out = (nsurv == 0);
+    if (screened_out) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
+
+    if constexpr (LB == 0 && !FOCK) {
+      // final integrals are (a 0|c d): row lanes own contiguous runs of the output
+      if (valid && rmeta.row >= K::ROW0) {
+        const int ab = rmeta.row - K::ROW0;
+        double* __restrict__ o = p.out + (size_t)task * p.out_stride;
+        if (!p.transpose_out) {
+          static_for<K::NCD>([&](auto ic) { o[ab * K::NCD + decltype(ic)::value] = H[decltype(ic)::value]; });
+        } else {
+          static_for<K::NCD>([&](auto ic) { o[decltype(ic)::value * K::NAB + ab] = H[decltype(ic)::value]; });
+        }
+      }
+    } else {
+      // ---- hand the rows over to (quartet, cd) lanes ------------------------------------
+      // (the K loop ended with a barrier, or had no shared traffic: the region is free)
+      constexpr int TBOFF = FOCK ? K::OFF_B2 : K::HDR;
+      if (valid && rmeta.row == 0) {
+        Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+      }
+      if constexpr (LB > 0) {
+        if (valid && rmeta.row >= K::ROW0)
+          static_for<K::NCD>([&](auto ic) {
+            Q[TBOFF + decltype(ic)::value * K::RTP + (rmeta.row - K::ROW0)] = H[decltype(ic)::value];
+          });
+      } else {  // Fock mode, LB == 0: rows go straight into the final [ab][cd] buffer
+        if (valid && rmeta.row >= K::ROW0)
+          static_for<K::NCD>([&](auto ic) {
+            Q[K::HDR + (rmeta.row - K::ROW0) * K::CS + decltype(ic)::value] = H[decltype(ic)::value];
+          });
+      }
+      __syncthreads();
+      if constexpr (LB > 0) {
+        // ---- bra HRR in registers: (a b|c d) from (e 0|c d), hrr.h:246 -------------------
+        for (int item = tid; item < QPC * K::NCD; item += THREADS) {
+          const int q2 = item / K::NCD, cd = item - q2 * K::NCD;
+          const unsigned task2 = base + q2;
+          if (task2 >= ntasks) continue;
+          const double* Q2 = smem + (size_t)q2 * QSIZE;
+          const double ABv[3] = {Q2[0], Q2[1], Q2[2]};
+          double colin[K::NRT];
+          static_for<K::NRT>([&](auto rc) {
+            colin[decltype(rc)::value] = Q2[TBOFF + cd * K::RTP + decltype(rc)::value];
+          });
+          double O[K::NAB];
+          rr_hrr_regs<LA, LB>(colin, ABv, O);
+          if constexpr (!FOCK) {
+            double* __restrict__ o = p.out + (size_t)task2 * p.out_stride;
+            if (!p.transpose_out) {
+              static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
+            } else {
+              static_for<K::NAB>([&](auto ic) { o[cd * K::NAB + decltype(ic)::value] = O[decltype(ic)::value]; });
+            }
+          } else {
+            double* fin = const_cast<double*>(Q2) + K::HDR;
+            static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
+          }
+        }
+        if constexpr (FOCK) __syncthreads();
+      }
+      if constexpr (FOCK) {
+        // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet --------
+        fock_digest<LA, LB, LC, LD, NEC>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
+                                         Q + K::OFF_B2, ib, ik, deg);
+      }
+    }
+  }
+}
+
+}  // namespace lb200

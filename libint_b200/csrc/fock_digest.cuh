@@ -1,0 +1,141 @@
+// cart -> pure transform and 6-way J/K digestion of one shell quartet held in shared memory,
+// executed by the T lanes that own the quartet; every thread of the CTA must call it (it
+// contains CTA-wide barriers), lanes of idle quartets with active == false.
+//
+// Reference: tests/hartree-fock/hartree-fock++.cc:1703-1743 (g_12 += D_34 v, g_34 += D_12 v,
+// g_13 -= D_24 v/4, g_24 -= D_13 v/4, g_14 -= D_23 v/4, g_23 -= D_14 v/4, v = (12|34) deg)
+// and the solid-harmonic transform Engine::compute2 applies before returning
+// (engine.impl.h:1965-1985, solidharmonics.h:281-463; standard convention pure iff l >= 2).
+#pragma once
+#include "eri_kernel.cuh"
+
+namespace lb200 {
+
+template <int LA, int LB, int LC, int LD, int T>
+__device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int lane,
+                                            double* __restrict__ fin /* [NAB][CS] */, int,
+                                            double* __restrict__ buf2 /* NAB*NCD dense */, int ib,
+                                            int ik, double deg) {
+  constexpr int NA = nc(LA), NB = nc(LB), NC = nc(LC), ND = nc(LD), NCD = NC * ND, CS = NCD | 1;
+  constexpr int PA_ = LA >= 2, PB_ = LB >= 2, PC_ = LC >= 2, PD_ = LD >= 2;
+  constexpr int na = PA_ ? npure(LA) : NA, nb = PB_ ? npure(LB) : NB;
+  constexpr int nc_ = PC_ ? npure(LC) : NC, nd = PD_ ? npure(LD) : ND;
+  constexpr int NPASS = PA_ + PB_ + PC_ + PD_;
+  auto fin_at = [&](int ab, int cd) -> double { return fin[ab * CS + cd]; };
+  // pass n reads: n == 0 the strided HRR layout, n odd buf2, n even (>0) the dense fin region;
+  // writes: n even buf2, n odd the fin region (dense)
+  if constexpr (PA_) {
+    if (active)
+      pure_pass<T, LA, 1, NB * NCD>(
+          lane,
+          [&](int, int k, int in) {
+            const int b = in / NCD, cd = in - b * NCD;
+            return fin_at(k * NB + b, cd);
+          },
+          buf2);
+    __syncthreads();
+  }
+  if constexpr (PB_) {
+    constexpr int n = PA_;
+    double* out = (n % 2 == 0) ? buf2 : fin;
+    if (active) {
+      if constexpr (n == 0) {
+        pure_pass<T, LB, na, NCD>(lane, [&](int o, int k, int in) { return fin_at(o * NB + k, in); }, out);
+      } else {
+        const double* in_ = buf2;
+        pure_pass<T, LB, na, NCD>(lane, [&](int o, int k, int in) { return in_[(o * NB + k) * NCD + in]; }, out);
+      }
+    }
+    __syncthreads();
+  }
+  if constexpr (PC_) {
+    constexpr int n = PA_ + PB_;
+    double* out = (n % 2 == 0) ? buf2 : fin;
+    if (active) {
+      if constexpr (n == 0) {
+        pure_pass<T, LC, na * nb, ND>(lane, [&](int o, int k, int in) { return fin_at(o, k * ND + in); }, out);
+      } else {
+        const double* in_ = (n % 2 == 1) ? buf2 : fin;
+        pure_pass<T, LC, na * nb, ND>(lane, [&](int o, int k, int in) { return in_[(o * NC + k) * ND + in]; }, out);
+      }
+    }
+    __syncthreads();
+  }
+  if constexpr (PD_) {
+    constexpr int n = PA_ + PB_ + PC_;
+    double* out = (n % 2 == 0) ? buf2 : fin;
+    if (active) {
+      if constexpr (n == 0) {
+        pure_pass<T, LD, na * nb * nc_, 1>(
+            lane,
+            [&](int o, int k, int) {
+              const int ab = o / NC, c = o - ab * NC;
+              return fin_at(ab, c * ND + k);
+            },
+            out);
+      } else {
+        const double* in_ = (n % 2 == 1) ? buf2 : fin;
+        pure_pass<T, LD, na * nb * nc_, 1>(lane, [&](int o, int k, int) { return in_[o * ND + k]; }, out);
+      }
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+  const double* cur = (NPASS % 2 == 1) ? buf2 : fin;
+  auto I = [&](int a, int b, int c, int d) -> double {
+    if constexpr (NPASS > 0)
+      return cur[((a * nb + b) * nc_ + c) * nd + d];
+    else
+      return fin_at(a * nb + b, c * nd + d);
+  };
+  const int bfa = p.bra.bf[2 * ib], bfb = p.bra.bf[2 * ib + 1];
+  const int bfc = p.ket.bf[2 * ik], bfd = p.ket.bf[2 * ik + 1];
+  const int n = p.nbf;
+  const double* __restrict__ D = p.D;
+  double* __restrict__ F = p.F;
+  for (int i = lane; i < na * nb; i += T) {  // F(a,b) += D(c,d) v
+    const int a = i / nb, b = i - a * nb;
+    double s = 0.0;
+    for (int c = 0; c < nc_; ++c)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfc + c) * n + bfd + d]);
+    atomicAdd(&F[(bfa + a) * n + bfb + b], s * deg);
+  }
+  for (int i = lane; i < nc_ * nd; i += T) {  // F(c,d) += D(a,b) v
+    const int c = i / nd, d = i - c * nd;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfb + b]);
+    atomicAdd(&F[(bfc + c) * n + bfd + d], s * deg);
+  }
+  const double kdeg = -0.25 * deg;
+  for (int i = lane; i < na * nc_; i += T) {  // F(a,c) -= 1/4 D(b,d) v
+    const int a = i / nc_, c = i - a * nc_;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfb + b) * n + bfd + d]);
+    atomicAdd(&F[(bfa + a) * n + bfc + c], s * kdeg);
+  }
+  for (int i = lane; i < nb * nd; i += T) {  // F(b,d) -= 1/4 D(a,c) v
+    const int b = i / nd, d = i - b * nd;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfc + c]);
+    atomicAdd(&F[(bfb + b) * n + bfd + d], s * kdeg);
+  }
+  for (int i = lane; i < na * nd; i += T) {  // F(a,d) -= 1/4 D(b,c) v
+    const int a = i / nd, d = i - a * nd;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b)
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * __ldg(&D[(bfb + b) * n + bfc + c]);
+    atomicAdd(&F[(bfa + a) * n + bfd + d], s * kdeg);
+  }
+  for (int i = lane; i < nb * nc_; i += T) {  // F(b,c) -= 1/4 D(a,d) v
+    const int b = i / nc_, c = i - b * nc_;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfd + d]);
+    atomicAdd(&F[(bfb + b) * n + bfc + c], s * kdeg);
+  }
+}
+
+}  // namespace lb200

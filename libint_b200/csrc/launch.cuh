@@ -1,20 +1,30 @@
-// Host-side launcher of one class kernel (explicitly instantiated in gen/eri_inst_*.cu).
+// Host-side launchers of one class (explicitly instantiated in gen/eri_inst_*.cu).
+//
+// Two kernel families serve a class (X|Y) (X = the pair class with the larger order key):
+//   * eri_rowreg_kernel (eri_rowreg.cuh): rows = the smaller pair, the other pair unrolled in
+//     registers; used whenever the unrolled pair has l1+l2 <= 4;
+//   * eri_class_kernel (eri_kernel.cuh): all-shared-memory team kernel, the fallback for
+//     (fd|fd), (ff|fd), (ff|ff).
 #pragma once
 #include "eri_config.cuh"
+#include "eri_rowreg.cuh"
 
 namespace lb200 {
 
 template <int LA, int LB, int LC, int LD, int MODE>
-cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
-                         cudaStream_t stream) {
+cudaError_t launch_team(const EriParams& p, const RowInfo* rows, int num_sms, cudaStream_t stream) {
   using C = Cfg<LA, LB, LC, LD, MODE>;
   if constexpr (!C::FITS) {
     return cudaErrorInvalidConfiguration;
   } else {
     auto kern = eri_class_kernel<LA, LB, LC, LD, C::T, MODE>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::SMEM_BYTES);
-    if (err != cudaSuccess) return err;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_BYTES);
+      if (err != cudaSuccess) return err;
+      configured = true;
+    }
     long long grid = (long long)num_sms * C::CTAS_PER_SM;
     if (!p.ntasks_dev) {
       const long long need = ((long long)p.ntasks + C::TEAMS_PER_CTA - 1) / C::TEAMS_PER_CTA;
@@ -23,6 +33,50 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, stream>>>(p, rows);
     return cudaGetLastError();
+  }
+}
+
+template <int LA, int LB, int LC, int LD, int MODE>
+cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
+                          cudaStream_t stream) {
+  using K = RR<LA, LB, LC, LD>;
+  constexpr int SMEM = K::QPC * K::qsize(MODE == kModeFock) * 8;
+  static_assert(SMEM <= kSmemLimit, "row-register kernel exceeds shared memory");
+  auto kern = eri_rowreg_kernel<LA, LB, LC, LD, MODE>;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (err != cudaSuccess) return err;
+    int nb = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::THREADS, SMEM);
+    if (err != cudaSuccess) return err;
+    ctas_per_sm = nb < 1 ? 1 : nb;
+  }
+  long long grid = (long long)num_sms * ctas_per_sm;
+  if (!p.ntasks_dev) {
+    const long long need = ((long long)p.ntasks + K::QPC - 1) / K::QPC;
+    if (need < grid) grid = need;
+  }
+  if (grid < 1) return cudaSuccess;
+  kern<<<(unsigned)grid, K::THREADS, SMEM, stream>>>(p, rows);
+  return cudaGetLastError();
+}
+
+template <int LA, int LB, int LC, int LD, int MODE>
+cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
+                         cudaStream_t stream) {
+  if constexpr (LA + LB <= 4) {
+    // rows = (LC LD| (the smaller pair), (LA LB) unrolled: the kernel sees bra and ket swapped
+    EriParams q = p;
+    q.bra = p.ket;
+    q.ket = p.bra;
+    q.swap_tasks = p.swap_tasks ^ 1;
+    q.transpose_out = p.transpose_out ^ 1;
+    return launch_rowreg<LC, LD, LA, LB, MODE>(q, rows, num_sms, stream);
+  } else if constexpr (LC + LD <= 4) {
+    return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
+  } else {
+    return launch_team<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
   }
 }
 

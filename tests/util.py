@@ -44,3 +44,19 @@ def assert_parity(got, ref, what="", rtol=RTOL, atol=ATOL):
         raise AssertionError("%s: %d of %d elements outside %g rel / %g abs; worst at %d: got %.17g "
                              "ref %.17g (abs err %.3g)" % (what, bad.sum(), len(ref), rtol, atol, i,
                                                            got[i], ref[i], err[i]))
+
+
+def hrr_amplification(l, O):
+    """Conditioning of the horizontal recurrence for one shell set: the HGP scheme forms
+    (a b| = sum_k C(lb,k) AB^k (a+lb-k 0| (src/bin/libint/hrr.h:246,324), so rounding noise of
+    the contracted (e0|f0) intermediates is amplified by up to (1+|AB|)^lb (1+|CD|)^ld in the
+    final integrals -- for the reference's generated code as for ours (tests/eri/test.cc:77-83
+    notes the same loss for (dp|dd), (dd|dd)).  The absolute tolerance of a parity check between
+    two different operation orders is scaled by this factor."""
+    O = np.asarray(O, dtype=np.float64).reshape(-1, 3)
+    ab = np.linalg.norm(O[0] - O[1])
+    amp = (1.0 + ab) ** min(l[0], l[1])
+    if len(l) == 4:
+        cd = np.linalg.norm(O[2] - O[3])
+        amp *= (1.0 + cd) ** min(l[2], l[3])
+    return amp
