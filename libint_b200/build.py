@@ -14,13 +14,17 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+# experiment knobs: LB200_LIB_SUFFIX builds a variant library next to the default one,
+# LB200_EXTRA_FLAGS appends nvcc flags (e.g. -DLB200_RR_MINB=3)
+SUFFIX = os.environ.get("LB200_LIB_SUFFIX", "")
 OUT = os.path.join(HERE, "_lib")
-OBJ = os.path.join(OUT, "obj")
-LIB = os.path.join(OUT, "liblibint_b200.so")
+OBJ = os.path.join(OUT, "obj" + SUFFIX)
+LIB = os.path.join(OUT, "liblibint_b200%s.so" % SUFFIX)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-fvisibility=default", "-Wno-deprecated-gpu-targets"] + ARCH
+              "-Xcompiler", "-fvisibility=default", "-Wno-deprecated-gpu-targets"] + ARCH + \
+    os.environ.get("LB200_EXTRA_FLAGS", "").split()
 BOYS = os.path.join(HERE, "data", "boys_cheb7_m24.bin")
 
 

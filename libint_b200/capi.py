@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "liblibint_b200.so")
+LIB_PATH = os.path.join(HERE, "_lib", "liblibint_b200%s.so" % os.environ.get("LB200_LIB_SUFFIX", ""))
 
 OK = 0
 SCREEN_ORIGINAL = 0x0001

@@ -62,8 +62,9 @@ struct RR {
   // row->column transpose buffer and afterwards by the cart->pure passes
   static constexpr int OFF_B2 = HDR + NAB * CS;
   static constexpr int FOCK_DOUBLES = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);
+  static constexpr int STORE_DOUBLES = OFF_B2 + (LB > 0 ? NCD * RTP : 0);
   static constexpr int qsize(bool fock) {
-    int s = cmax(PRIM_DOUBLES, TB_DOUBLES);
+    int s = cmax(PRIM_DOUBLES, STORE_DOUBLES);
     if (fock) s = cmax(s, FOCK_DOUBLES);
     return (s + 1) & ~1;
   }
@@ -202,8 +203,11 @@ __device__ __forceinline__ double sel3(int d, double x, double y, double z) {
   return d == 0 ? x : (d == 1 ? y : z);
 }
 
+#ifndef LB200_RR_MINB
+#define LB200_RR_MINB 1
+#endif
 template <int LA, int LB, int LC, int LD, int MODE>
-__global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS)
+__global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS, LB200_RR_MINB)
 eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   using K = RRK<LA, LB, LC, LD>;
   constexpr bool FOCK = (MODE == kModeFock);
@@ -442,21 +446,10 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const bool screened_out = (nsurv == 0);
     if (screened_out) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
 
-    if constexpr (LB == 0 && !FOCK) {
-      // final integrals are (a 0|c d): row lanes own contiguous runs of the output
-      if (valid && rmeta.row >= K::ROW0) {
-        const int ab = rmeta.row - K::ROW0;
-        double* __restrict__ o = p.out + (size_t)task * p.out_stride;
-        if (!p.transpose_out) {
-          static_for<K::NCD>([&](auto ic) { o[ab * K::NCD + decltype(ic)::value] = H[decltype(ic)::value]; });
-        } else {
-          static_for<K::NCD>([&](auto ic) { o[decltype(ic)::value * K::NAB + ab] = H[decltype(ic)::value]; });
-        }
-      }
-    } else {
+    {
       // ---- hand the rows over to (quartet, cd) lanes ------------------------------------
       // (the K loop ended with a barrier, or had no shared traffic: the region is free)
-      constexpr int TBOFF = FOCK ? K::OFF_B2 : K::HDR;
+      constexpr int TBOFF = K::OFF_B2;
       if (valid && rmeta.row == 0) {
         Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
       }
@@ -465,7 +458,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           static_for<K::NCD>([&](auto ic) {
             Q[TBOFF + decltype(ic)::value * K::RTP + (rmeta.row - K::ROW0)] = H[decltype(ic)::value];
           });
-      } else {  // Fock mode, LB == 0: rows go straight into the final [ab][cd] buffer
+      } else {  // LB == 0: the rows are the final (a 0|c d) integrals
         if (valid && rmeta.row >= K::ROW0)
           static_for<K::NCD>([&](auto ic) {
             Q[K::HDR + (rmeta.row - K::ROW0) * K::CS + decltype(ic)::value] = H[decltype(ic)::value];
@@ -476,9 +469,8 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         // ---- bra HRR in registers: (a b|c d) from (e 0|c d), hrr.h:246 -------------------
         for (int item = tid; item < QPC * K::NCD; item += THREADS) {
           const int q2 = item / K::NCD, cd = item - q2 * K::NCD;
-          const unsigned task2 = base + q2;
-          if (task2 >= ntasks) continue;
-          const double* Q2 = smem + (size_t)q2 * QSIZE;
+          if (base + q2 >= ntasks) continue;
+          double* Q2 = smem + (size_t)q2 * QSIZE;
           const double ABv[3] = {Q2[0], Q2[1], Q2[2]};
           double colin[K::NRT];
           static_for<K::NRT>([&](auto rc) {
@@ -486,21 +478,41 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           });
           double O[K::NAB];
           rr_hrr_regs<LA, LB>(colin, ABv, O);
-          if constexpr (!FOCK) {
-            double* __restrict__ o = p.out + (size_t)task2 * p.out_stride;
-            if (!p.transpose_out) {
-              static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
-            } else {
-              static_for<K::NAB>([&](auto ic) { o[cd * K::NAB + decltype(ic)::value] = O[decltype(ic)::value]; });
-            }
+          if (!FOCK && !p.transpose_out) {
+            // natural orientation: lanes of a warp are adjacent in cd -> coalesced rows
+            double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
+            static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
           } else {
-            double* fin = const_cast<double*>(Q2) + K::HDR;
+            double* fin = Q2 + K::HDR;
             static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
           }
         }
-        if constexpr (FOCK) __syncthreads();
+        if (FOCK || p.transpose_out) __syncthreads();
       }
-      if constexpr (FOCK) {
+      if constexpr (!FOCK) {
+        // ---- coalesced copy-out: the round's quartets are one contiguous run of the output
+        // (layout ((a*nb+b)*nc+c)*nd+d per shell set, doc/progman/progman.tex:472-474; [cd][ab]
+        // when the caller's bra is this kernel's unrolled side) -----------------------------
+        constexpr int BLK = K::NAB * K::NCD;
+        const unsigned left = ntasks - base;
+        const int nvalid = left < (unsigned)QPC ? (int)left : QPC;
+        double* __restrict__ o = p.out + (size_t)base * BLK;
+        if (!p.transpose_out) {
+          if constexpr (LB == 0) {
+            for (int idx = tid; idx < nvalid * BLK; idx += THREADS) {
+              const int q2 = idx / BLK, i = idx - q2 * BLK;
+              const int ab = i / K::NCD, cd = i - ab * K::NCD;
+              o[idx] = smem[(size_t)q2 * QSIZE + K::HDR + ab * K::CS + cd];
+            }
+          }
+        } else {
+          for (int idx = tid; idx < nvalid * BLK; idx += THREADS) {
+            const int q2 = idx / BLK, i = idx - q2 * BLK;
+            const int cd = i / K::NAB, ab = i - cd * K::NAB;
+            o[idx] = smem[(size_t)q2 * QSIZE + K::HDR + ab * K::CS + cd];
+          }
+        }
+      } else {
         // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet --------
         fock_digest<LA, LB, LC, LD, NEC>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
                                          Q + K::OFF_B2, ib, ik, deg);
