@@ -94,7 +94,7 @@ struct RowMeta {   // per lane, fixed for the whole kernel
 template <class K, int F, class P1, class P2>
 __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p1, const P2& p2,
                                                const double (&QC)[3], const double (&WQ)[3],
-                                               const double (&koo2e)[4], double roe,
+                                               const double (&koo2e)[6], double roe,
                                                const double (&ce)[3], double* __restrict__ Xq,
                                                const RowMeta& rmeta, double* __restrict__ acc) {
   constexpr int NM = K::FMAX - F + 1;
@@ -213,7 +213,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   constexpr bool FOCK = (MODE == kModeFock);
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
   constexpr int QPC = K::QPC, QSIZE = K::qsize(FOCK), THREADS = K::THREADS;
-  static_assert(FMAX <= 4, "register pyramid is sized for LC+LD <= 4");
+  static_assert(FMAX <= 6, "register pyramid is written for LC+LD <= 6");
 
   extern __shared__ double smem[];
   __shared__ int s_maxit[3];  // rotating: slot r%3 is reduced in round r, slot (r+1)%3 re-zeroed
@@ -339,7 +339,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         rho = bp.gamma * kp.gamma * oogpq;
         Targ = PQ2 * rho;
       }
-      double PA[3], WP[3], QC[3], WQ[3], oo2z = 0, roz = 0, koo2e[4], roe = 0, ce[3];
+      double PA[3], WP[3], QC[3], WQ[3], oo2z = 0, roz = 0, koo2e[6], roe = 0, ce[3];
       if (on) {
         ++nsurv;
         const double gp = oogpq * bp.gamma, gq = oogpq * kp.gamma;
@@ -355,6 +355,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         roz = rho * bp.oog;
         const double oo2e = 0.5 * kp.oog;
         koo2e[0] = 0.0; koo2e[1] = oo2e; koo2e[2] = 2.0 * oo2e; koo2e[3] = 3.0 * oo2e;
+        koo2e[4] = 4.0 * oo2e; koo2e[5] = 5.0 * oo2e;
         roe = rho * kp.oog;
         const double oo2ze = 0.5 * oogpq;
         ce[0] = rmeta.q[0] * oo2ze; ce[1] = rmeta.q[1] * oo2ze; ce[2] = rmeta.q[2] * oo2ze;
@@ -362,7 +363,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         pfac = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) PA[d] = WP[d] = QC[d] = WQ[d] = ce[d] = 0.0;
-        koo2e[0] = koo2e[1] = koo2e[2] = koo2e[3] = 0.0;
+        koo2e[0] = koo2e[1] = koo2e[2] = koo2e[3] = koo2e[4] = koo2e[5] = 0.0;
       }
 
       // ---- Boys: lanes m of the quartet, then broadcast through shared memory ----------
@@ -431,6 +432,16 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
               if constexpr (EMAX > 0) __syncthreads();
               Lvl<FMAX, 4> l4;
               rr_build_level<K, 4>(l4, l3, l2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+              if constexpr (FMAX >= 5) {   // (fd|, (ff| unrolled: correct, but the pyramid spills
+                if constexpr (EMAX > 0) __syncthreads();
+                Lvl<FMAX, 5> l5;
+                rr_build_level<K, 5>(l5, l4, l3, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+                if constexpr (FMAX >= 6) {
+                  if constexpr (EMAX > 0) __syncthreads();
+                  Lvl<FMAX, 6> l6;
+                  rr_build_level<K, 6>(l6, l5, l4, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+                }
+              }
             }
           }
         }

@@ -1,40 +1,14 @@
 // Host-side launchers of one class (explicitly instantiated in gen/eri_inst_*.cu).
 //
-// Two kernel families serve a class (X|Y) (X = the pair class with the larger order key):
-//   * eri_rowreg_kernel (eri_rowreg.cuh): rows = the smaller pair, the other pair unrolled in
-//     registers; used whenever the unrolled pair has l1+l2 <= 4;
-//   * eri_class_kernel (eri_kernel.cuh): all-shared-memory team kernel, the fallback for
-//     (fd|fd), (ff|fd), (ff|ff).
+// A class (X|Y) (X = the pair class with the larger order key) is served by
+// eri_rowreg_kernel (eri_rowreg.cuh) with rows = the smaller pair and the other pair unrolled in
+// registers whenever X has l1+l2 <= 4; for the (fd|, (ff| bras the roles are exchanged.
 #pragma once
-#include "eri_config.cuh"
 #include "eri_rowreg.cuh"
 
 namespace lb200 {
 
-template <int LA, int LB, int LC, int LD, int MODE>
-cudaError_t launch_team(const EriParams& p, const RowInfo* rows, int num_sms, cudaStream_t stream) {
-  using C = Cfg<LA, LB, LC, LD, MODE>;
-  if constexpr (!C::FITS) {
-    return cudaErrorInvalidConfiguration;
-  } else {
-    auto kern = eri_class_kernel<LA, LB, LC, LD, C::T, MODE>;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES);
-      if (err != cudaSuccess) return err;
-      configured = true;
-    }
-    long long grid = (long long)num_sms * C::CTAS_PER_SM;
-    if (!p.ntasks_dev) {
-      const long long need = ((long long)p.ntasks + C::TEAMS_PER_CTA - 1) / C::TEAMS_PER_CTA;
-      if (need < grid) grid = need;
-    }
-    if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, stream>>>(p, rows);
-    return cudaGetLastError();
-  }
-}
+constexpr int kSmemLimit = 227 * 1024;  // usable dynamic shared memory per CTA on sm_100
 
 template <int LA, int LB, int LC, int LD, int MODE>
 cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
@@ -73,10 +47,10 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
     q.swap_tasks = p.swap_tasks ^ 1;
     q.transpose_out = p.transpose_out ^ 1;
     return launch_rowreg<LC, LD, LA, LB, MODE>(q, rows, num_sms, stream);
-  } else if constexpr (LC + LD <= 4) {
-    return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
   } else {
-    return launch_team<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
+    // (fd|, (ff| bras: rows = the big pair, the other pair unrolled (up to l1+l2 = 6; beyond 4
+    // the register pyramid spills to local memory -- these classes are rare)
+    return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
   }
 }
 

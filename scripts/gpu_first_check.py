@@ -21,8 +21,6 @@ pcs = [(a, b) for a in range(4) for b in range(a + 1)] + [(4, 0)]
 t0 = time.time()
 fails = []
 for (la, lb), (lc, ld) in itertools.product(pcs, pcs):
-    if (la, lb, lc, ld) == (3, 3, 3, 3):
-        continue
     K = 2 if la + lb + lc + ld <= 8 else 1
     l, pure, nprim, O, al, co = rand_basis([la, lb, lc, ld], K)
     bs = capi.Basis(ctx, l, pure, nprim, O, al, co)

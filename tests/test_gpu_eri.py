@@ -12,7 +12,7 @@ from util import (ATOL, PAIR_CLASSES, all_classes, assert_parity, hrr_amplificat
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # classes of the l<=3 (+ g-bra) grid without a kernel yet; must fail cleanly with an LMAX error
-KNOWN_GAPS = {(3, 3, 3, 3)}
+KNOWN_GAPS = set()
 
 
 def _supported(capi, cl):
