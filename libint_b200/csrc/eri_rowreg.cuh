@@ -75,7 +75,16 @@ struct RR {
     return 96;                   // NEC = 84: 1 quartet
   }
   static constexpr int THREADS = threads();
-  static constexpr int QPC = THREADS / NEC;           // quartets per CTA round
+  // sync group: for NEC <= 16 the quartets of a warp never leave it, every barrier is a
+  // __syncwarp and the warps of a CTA run independent rounds; larger NEC: the whole CTA
+  static constexpr bool WL = NEC <= 16;
+  static constexpr int GROUP = WL ? 32 : THREADS;
+  static constexpr int QPG = GROUP / NEC;             // quartets per group round
+  static constexpr int NG = THREADS / GROUP;
+  // CTAs per SM the register allocation is bounded for (measured per pyramid depth: the F = 4
+  // pyramid wants the full 255 registers, shallower ones gain more from a third / fourth CTA)
+  static constexpr int MINB = FMAX >= 4 ? 2 : (FMAX >= 2 ? 3 : 4);
+  static constexpr int QPC = NG * QPG;                // quartets in flight per CTA
 };
 
 // one level of the register pyramid: [row 0|f 0]^(m), component j, m = 0..FMAX-F
@@ -203,28 +212,33 @@ __device__ __forceinline__ double sel3(int d, double x, double y, double z) {
   return d == 0 ? x : (d == 1 ? y : z);
 }
 
-#ifndef LB200_RR_MINB
-#define LB200_RR_MINB 1
-#endif
 template <int LA, int LB, int LC, int LD, int MODE>
-__global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS, LB200_RR_MINB)
+__global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS, RR<LA, LB, LC, LD>::MINB)
 eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   using K = RRK<LA, LB, LC, LD>;
   constexpr bool FOCK = (MODE == kModeFock);
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
-  constexpr int QPC = K::QPC, QSIZE = K::qsize(FOCK), THREADS = K::THREADS;
+  constexpr int QSIZE = K::qsize(FOCK), THREADS = K::THREADS;
+  constexpr bool WL = K::WL;
+  constexpr int GROUP = K::GROUP, QPG = K::QPG, NG = K::NG;
   static_assert(FMAX <= 6, "register pyramid is written for LC+LD <= 6");
 
   extern __shared__ double smem[];
   __shared__ int s_maxit[3];  // rotating: slot r%3 is reduced in round r, slot (r+1)%3 re-zeroed
 
   const int tid = threadIdx.x;
-  const int q = tid / NEC;            // quartet slot of this lane
-  const bool lane_on = q < QPC;       // leftover lanes only take part in barriers and phase 2
+  const int g = WL ? tid >> 5 : 0;    // sync group of this lane
+  const int gl = WL ? tid & 31 : tid; // lane within the group
+  const int qg = gl / NEC;            // quartet slot within the group
+  const bool lane_on = qg < QPG;      // leftover lanes only take part in barriers and phase 2
+  const int q = g * QPG + qg;         // CTA-wide quartet slot (shared-memory region)
+  auto sync = [] {
+    if constexpr (WL) __syncwarp(); else __syncthreads();
+  };
   RowMeta rmeta;
   // leftover lanes get a row index past every "row < NECX" / "row >= ROW0" guarded write
   // (NEC <= 84 < kMaxRows: still a valid RowInfo index)
-  rmeta.row = lane_on ? tid - q * NEC : NEC;
+  rmeta.row = lane_on ? gl - qg * NEC : NEC;
   {
     const RowInfo ri = rows[rmeta.row];
     rmeta.e = ri.e;
@@ -254,11 +268,13 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   double* const Q = smem + (size_t)(lane_on ? q : 0) * QSIZE;  // this lane's quartet region
 
   const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
-  if (tid < 3) s_maxit[tid] = 0;
-  __syncthreads();
+  if constexpr (!WL) {
+    if (tid < 3) s_maxit[tid] = 0;
+    __syncthreads();
+  }
   int round = 0;
-  for (unsigned base = blockIdx.x * QPC; base < ntasks; base += gridDim.x * QPC) {
-    const unsigned task = base + q;
+  for (unsigned base = (blockIdx.x * NG + g) * QPG; base < ntasks; base += gridDim.x * NG * QPG) {
+    const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
     int ib = 0, ik = 0, pb0 = 0, nb = 0, pk0 = 0, nk = 0;
     if (valid) {
@@ -271,9 +287,11 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       nk = p.ket.prim_off[ik + 1] - pk0;
     }
     const int nit = nb * nk;
-    // slot (round+1)%3 was last read in round-2, i.e. before the barrier of round-1
-    if (tid == 0) s_maxit[(round + 1) % 3] = 0;
-    if (valid && rmeta.row == 0 && nit > 0) atomicMax(&s_maxit[round % 3], nit);
+    if constexpr (!WL) {
+      // slot (round+1)%3 was last read in round-2, i.e. before the barrier of round-1
+      if (tid == 0) s_maxit[(round + 1) % 3] = 0;
+      if (valid && rmeta.row == 0 && nit > 0) atomicMax(&s_maxit[round % 3], nit);
+    }
 
     // ---- per-quartet screening precision ----------------------------------------------
     double ln_prec = p.ln_precision, prec = p.precision, deg = 1.0;
@@ -308,8 +326,11 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     double acc[K::NFT];
     static_for<K::NFT>([&](auto ic) { acc[decltype(ic)::value] = 0.0; });
     int nsurv = 0;
-    __syncthreads();   // also separates the previous round's phase 2 from this round's writes
-    const int maxit = s_maxit[round % 3];
+    sync();   // also separates the previous round's phase 2 from this round's writes
+    int maxit;
+    if constexpr (NEC == 1) maxit = nit;   // no exchange inside the loop: private trip count
+    else if constexpr (WL) maxit = __reduce_max_sync(0xffffffffu, valid ? nit : 0);
+    else maxit = s_maxit[round % 3];
     ++round;
 
     for (int it = 0; it < maxit; ++it) {
@@ -377,7 +398,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         if (lane_on)
           for (int m = rmeta.row; m <= L; m += NEC)
             Q[K::OFF_F + m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
-        __syncthreads();
+        sync();
         static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] = Q[K::OFF_F + decltype(mc)::value]; });
       }
 
@@ -417,27 +438,27 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -------------------
       double* Xq = Q + K::OFF_X;
       if constexpr (FMAX >= 1) {
-        if constexpr (EMAX > 0) __syncthreads();
+        if constexpr (EMAX > 0) sync();
         Lvl<FMAX, 1> l1;
         rr_build_level<K, 1>(l1, l0, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
         if constexpr (FMAX >= 2) {
-          if constexpr (EMAX > 0) __syncthreads();
+          if constexpr (EMAX > 0) sync();
           Lvl<FMAX, 2> l2;
           rr_build_level<K, 2>(l2, l1, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
           if constexpr (FMAX >= 3) {
-            if constexpr (EMAX > 0) __syncthreads();
+            if constexpr (EMAX > 0) sync();
             Lvl<FMAX, 3> l3;
             rr_build_level<K, 3>(l3, l2, l1, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
             if constexpr (FMAX >= 4) {
-              if constexpr (EMAX > 0) __syncthreads();
+              if constexpr (EMAX > 0) sync();
               Lvl<FMAX, 4> l4;
               rr_build_level<K, 4>(l4, l3, l2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
               if constexpr (FMAX >= 5) {   // (fd|, (ff| unrolled: correct, but the pyramid spills
-                if constexpr (EMAX > 0) __syncthreads();
+                if constexpr (EMAX > 0) sync();
                 Lvl<FMAX, 5> l5;
                 rr_build_level<K, 5>(l5, l4, l3, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
                 if constexpr (FMAX >= 6) {
-                  if constexpr (EMAX > 0) __syncthreads();
+                  if constexpr (EMAX > 0) sync();
                   Lvl<FMAX, 6> l6;
                   rr_build_level<K, 6>(l6, l5, l4, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
                 }
@@ -448,7 +469,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       }
       // the next iteration's first shared write (Boys values / level-0 cross values) must not
       // overtake this iteration's last cross-term reads
-      if constexpr (EMAX > 0) __syncthreads();
+      if constexpr (EMAX > 0) sync();
     }
 
     // ---- ket HRR in registers: (row 0|c d) from (row 0|f 0), hrr.h:324 -------------------
@@ -475,13 +496,13 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
             Q[K::HDR + (rmeta.row - K::ROW0) * K::CS + decltype(ic)::value] = H[decltype(ic)::value];
           });
       }
-      __syncthreads();
+      sync();
       if constexpr (LB > 0) {
         // ---- bra HRR in registers: (a b|c d) from (e 0|c d), hrr.h:246 -------------------
-        for (int item = tid; item < QPC * K::NCD; item += THREADS) {
+        for (int item = gl; item < QPG * K::NCD; item += GROUP) {
           const int q2 = item / K::NCD, cd = item - q2 * K::NCD;
           if (base + q2 >= ntasks) continue;
-          double* Q2 = smem + (size_t)q2 * QSIZE;
+          double* Q2 = smem + (size_t)(g * QPG + q2) * QSIZE;
           const double ABv[3] = {Q2[0], Q2[1], Q2[2]};
           double colin[K::NRT];
           static_for<K::NRT>([&](auto rc) {
@@ -498,7 +519,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
             static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
           }
         }
-        if (FOCK || p.transpose_out) __syncthreads();
+        if (FOCK || p.transpose_out) sync();
       }
       if constexpr (!FOCK) {
         // ---- coalesced copy-out: the round's quartets are one contiguous run of the output
@@ -506,26 +527,26 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         // when the caller's bra is this kernel's unrolled side) -----------------------------
         constexpr int BLK = K::NAB * K::NCD;
         const unsigned left = ntasks - base;
-        const int nvalid = left < (unsigned)QPC ? (int)left : QPC;
+        const int nvalid = left < (unsigned)QPG ? (int)left : QPG;
         double* __restrict__ o = p.out + (size_t)base * BLK;
         if (!p.transpose_out) {
           if constexpr (LB == 0) {
-            for (int idx = tid; idx < nvalid * BLK; idx += THREADS) {
+            for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
               const int q2 = idx / BLK, i = idx - q2 * BLK;
               const int ab = i / K::NCD, cd = i - ab * K::NCD;
-              o[idx] = smem[(size_t)q2 * QSIZE + K::HDR + ab * K::CS + cd];
+              o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::HDR + ab * K::CS + cd];
             }
           }
         } else {
-          for (int idx = tid; idx < nvalid * BLK; idx += THREADS) {
+          for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
             const int q2 = idx / BLK, i = idx - q2 * BLK;
             const int cd = i / K::NAB, ab = i - cd * K::NAB;
-            o[idx] = smem[(size_t)q2 * QSIZE + K::HDR + ab * K::CS + cd];
+            o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::HDR + ab * K::CS + cd];
           }
         }
       } else {
         // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet --------
-        fock_digest<LA, LB, LC, LD, NEC>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
+        fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
                                          Q + K::OFF_B2, ib, ik, deg);
       }
     }

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -404,6 +406,12 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   }
   double nquartets = 0, ncand = 0;
   std::vector<unsigned> jmax;
+  // LB200_FOCK_PROFILE=1: per class-pair device time (one sync per launch; diagnostics only)
+  const bool profile = stats && std::getenv("LB200_FOCK_PROFILE");
+  struct Prof { int c[4]; double ms, nq; };
+  std::vector<Prof> prof;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const size_t ncls = f->classes.size();
   for (size_t X = 0; X < ncls && !rc; ++X)
     for (size_t Y = 0; Y <= X && !rc; ++Y) {
@@ -465,9 +473,24 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.fock_precision = fock_precision;
           p.needed_engine_precision = needed_engine_precision;
           p.ln_needed_engine_precision = std::log(needed_engine_precision);
+          if (profile) cudaEventRecord(pe0, st);
           rc = check_cuda(ctx, launch_eri(B.la, B.lb, Kt.la, Kt.lb, p, ctx->d_rows, kModeFock,
                                           ctx->num_sms, st), "launch fock kernel");
           ++ctx->launches;
+          if (profile) {
+            cudaEventRecord(pe1, st);
+            cudaEventSynchronize(pe1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pe0, pe1);
+            unsigned c = 0;
+            cudaMemcpy(&c, f->d_count, 4, cudaMemcpyDeviceToHost);
+            bool found = false;
+            for (auto& e : prof)
+              if (e.c[0] == B.la && e.c[1] == B.lb && e.c[2] == Kt.la && e.c[3] == Kt.lb) {
+                e.ms += ms; e.nq += c; found = true;
+              }
+            if (!found) prof.push_back(Prof{{B.la, B.lb, Kt.la, Kt.lb}, ms, (double)c});
+          }
           if (stats) {  // optional accounting costs a sync per chunk
             unsigned c = 0;
             cudaMemcpyAsync(&c, f->d_count, 4, cudaMemcpyDeviceToHost, st);
@@ -479,6 +502,17 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
       }
     }
   if (rc) return rc;
+  if (profile) {
+    std::sort(prof.begin(), prof.end(), [](const Prof& a, const Prof& b) { return a.ms > b.ms; });
+    double tot = 0;
+    for (auto& e : prof) tot += e.ms;
+    std::fprintf(stderr, "lb200 fock profile: %zu class pairs, %.2f ms in class kernels\n", prof.size(), tot);
+    for (auto& e : prof)
+      std::fprintf(stderr, "  (%d%d|%d%d) %10.3f ms %5.1f%% %12.0f quartets %8.2f ns/quartet\n", e.c[0], e.c[1],
+                   e.c[2], e.c[3], e.ms, 100 * e.ms / tot, e.nq, e.nq > 0 ? 1e6 * e.ms / e.nq : 0.0);
+    cudaEventDestroy(pe0);
+    cudaEventDestroy(pe1);
+  }
   double* d_G = nullptr;
   if (G_on_device) {
     symmetrize_kernel<<<std::min(4096ll, (long long)(n2 + 255) / 256), 256, 0, st>>>(f->d_F, G, n);

@@ -1,6 +1,6 @@
 // cart -> pure transform and 6-way J/K digestion of one shell quartet held in shared memory,
-// executed by the T lanes that own the quartet; every thread of the CTA must call it (it
-// contains CTA-wide barriers), lanes of idle quartets with active == false.
+// executed by the T lanes that own the quartet; every thread of the sync group (warp if
+// WARP_SYNC, else CTA) must call it, lanes of idle quartets with active == false.
 //
 // Reference: tests/hartree-fock/hartree-fock++.cc:1703-1743 (g_12 += D_34 v, g_34 += D_12 v,
 // g_13 -= D_24 v/4, g_24 -= D_13 v/4, g_14 -= D_23 v/4, g_23 -= D_14 v/4, v = (12|34) deg)
@@ -11,7 +11,7 @@
 
 namespace lb200 {
 
-template <int LA, int LB, int LC, int LD, int T>
+template <int LA, int LB, int LC, int LD, int T, bool WARP_SYNC>
 __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int lane,
                                             double* __restrict__ fin /* [NAB][CS] */, int,
                                             double* __restrict__ buf2 /* NAB*NCD dense */, int ib,
@@ -22,6 +22,9 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
   constexpr int nc_ = PC_ ? npure(LC) : NC, nd = PD_ ? npure(LD) : ND;
   constexpr int NPASS = PA_ + PB_ + PC_ + PD_;
   auto fin_at = [&](int ab, int cd) -> double { return fin[ab * CS + cd]; };
+  auto sync = [] {
+    if constexpr (WARP_SYNC) __syncwarp(); else __syncthreads();
+  };
   // pass n reads: n == 0 the strided HRR layout, n odd buf2, n even (>0) the dense fin region;
   // writes: n even buf2, n odd the fin region (dense)
   if constexpr (PA_) {
@@ -33,7 +36,7 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
             return fin_at(k * NB + b, cd);
           },
           buf2);
-    __syncthreads();
+    sync();
   }
   if constexpr (PB_) {
     constexpr int n = PA_;
@@ -46,7 +49,7 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
         pure_pass<T, LB, na, NCD>(lane, [&](int o, int k, int in) { return in_[(o * NB + k) * NCD + in]; }, out);
       }
     }
-    __syncthreads();
+    sync();
   }
   if constexpr (PC_) {
     constexpr int n = PA_ + PB_;
@@ -59,7 +62,7 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
         pure_pass<T, LC, na * nb, ND>(lane, [&](int o, int k, int in) { return in_[(o * NC + k) * ND + in]; }, out);
       }
     }
-    __syncthreads();
+    sync();
   }
   if constexpr (PD_) {
     constexpr int n = PA_ + PB_ + PC_;
@@ -78,7 +81,7 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
         pure_pass<T, LD, na * nb * nc_, 1>(lane, [&](int o, int k, int) { return in_[o * ND + k]; }, out);
       }
     }
-    __syncthreads();
+    sync();
   }
   if (!active) return;
   const double* cur = (NPASS % 2 == 1) ? buf2 : fin;
