@@ -288,6 +288,14 @@ H2O_XYZ_ANGSTROM = [(8, (0.00000, -0.07579, 0.00000)), (1, (0.86681, 0.60144, 0.
                     (1, (-0.86681, 0.60144, 0.00000))]  # tests/hartree-fock/h2o.xyz
 
 
+# tests/hartree-fock/h2o_rotated.xyz (h2o.xyz rotated by EulerMatrix[{pi/4,pi/6,pi/6}]), Angstrom:
+# the default geometry of the reference's hartree-fock++ validation run
+H2O_ROTATED_XYZ_ANGSTROM = [(8, (-0.06698952868266053, -0.02320585345069213, -0.026795811473064216)),
+                            (1, (0.6848346853461241, -0.6120631876157682, 0.5191047657385741)),
+                            (1, (0.37837107084596855, 0.9803684653406467, -0.09382246326173704))]
+BOHR_TO_ANGSTROM_CODATA2010 = 0.52917721092  # atom.h:63; what tests/hartree-fock/hartree-fock.cc:306 uses
+
+
 def _random_rotation(rng):
     q = rng.standard_normal(4)
     q /= np.linalg.norm(q)

@@ -1,0 +1,113 @@
+"""Restricted Hartree-Fock driver around the GPU Fock build: the consumer that the reference's
+tests/hartree-fock/hartree-fock++.cc is for libint (main(), :233-520).
+
+Same steps and conventions as the reference driver: nuclear repulsion (:245-255), S/T/V
+(:267-275), conditioned orthogonalizer X with XtX condition number (:281-290, :1957-2006),
+core-Hamiltonian start (:300-303 when the basis is minimal; the reference's SOAD start for
+larger bases converges to the same ground state), density D = C_occ C_occ^T, energy
+E = sum D o (H + F) + E_nuc (:472), commutator error ||FDS - SDF|| / n^2 (:476-477), DIIS
+(diis.h) and the "totally empirical" Fock precision schedule (:463-466).  The two-electron
+part F - H = G(D) comes from `fock_builder`, any callable (D, precision) -> G: the GPU
+FockBuilder in production; tests also feed the CPU oracle's G through the same loop to pin the
+oracle against the reference's golden energies.
+"""
+import numpy as np
+
+from . import onebody
+
+
+class DIIS:
+    """libint2::DIIS (include/libint2/diis.h): Pulay extrapolation over the last `ndiis`
+    (Fock, error) pairs, started after `strt` iterations."""
+
+    def __init__(self, strt=2, ndiis=5):
+        self.strt, self.ndiis = strt, ndiis
+        self.x, self.e = [], []
+        self.iter = 0
+
+    def extrapolate(self, F, err):
+        self.iter += 1
+        self.x.append(F.copy())
+        self.e.append(err.copy())
+        if len(self.x) > self.ndiis:
+            self.x.pop(0)
+            self.e.pop(0)
+        n = len(self.x)
+        if self.iter < self.strt or n < 2:
+            return F
+        B = np.empty((n + 1, n + 1))
+        for i in range(n):
+            for j in range(n):
+                B[i, j] = float(np.vdot(self.e[i], self.e[j]))
+        scale = max(abs(B[:n, :n]).max(), 1e-300)
+        B[:n, :n] /= scale
+        B[n, :n] = B[:n, n] = -1.0
+        B[n, n] = 0.0
+        rhs = np.zeros(n + 1)
+        rhs[n] = -1.0
+        try:
+            c = np.linalg.solve(B, rhs)[:n]
+        except np.linalg.LinAlgError:
+            return F
+        return sum(ci * xi for ci, xi in zip(c, self.x))
+
+
+def conditioning_orthogonalizer(S, max_condition_number=1e8):
+    """-> (X, Xinv-less) = (S^-1/2 restricted to the well-conditioned subspace, rank, condition
+    number of the retained part); gensqrtinv of hartree-fock++.cc:1957-2006."""
+    w, U = np.linalg.eigh(S)
+    wmax = w[-1]
+    keep = w >= wmax / max_condition_number
+    cond = wmax / w[keep][0]
+    X = U[:, keep] / np.sqrt(w[keep])
+    return X, int(keep.sum()), float(cond)
+
+
+class RHF:
+    def __init__(self, obs, atoms, fock_builder, charge=0):
+        self.obs, self.atoms, self.fock_builder = obs, atoms, fock_builder
+        nelec = sum(a.atomic_number for a in atoms) - charge
+        if nelec % 2:
+            raise ValueError("RHF needs an even number of electrons")
+        self.ndocc = nelec // 2
+        self.enuc = onebody.nuclear_repulsion(atoms)
+        self.S, self.T, self.V = onebody.compute_1body_ints(obs, atoms)
+        self.H = self.T + self.V
+        self.X, self.rank, self.cond = conditioning_orthogonalizer(self.S)
+        self.history = []
+        self.energy = None
+        self.D = self._density(self.H)
+
+    def _density(self, F):
+        e, Cp = np.linalg.eigh(self.X.T @ F @ self.X)
+        self.evals = e
+        self.C = self.X @ Cp
+        Co = self.C[:, :self.ndocc]
+        return Co @ Co.T
+
+    def run(self, conv=1e-12, maxiter=100, verbose=False):
+        H, S = self.H, self.S
+        n2 = H.size
+        diis = DIIS(2)
+        D = self.D
+        ehf, rms, it = 0.0, 1.0, 0
+        eps = np.finfo(float).eps
+        while True:
+            it += 1
+            ehf_last = ehf
+            precision = min(min(1e-3 / self.cond, 1e-7), max(rms / 1e4, eps))
+            F = H + np.asarray(self.fock_builder(D, precision))
+            ehf = float(np.sum(D * (H + F)))
+            ediff_rel = abs((ehf - ehf_last) / ehf)
+            comm = F @ D @ S - S @ D @ F
+            rms = float(np.linalg.norm(comm)) / n2
+            D = self._density(diis.extrapolate(F, comm))
+            self.history.append((it, ehf + self.enuc, ediff_rel, rms))
+            if verbose:
+                print(" %02d %20.12f %20.12e %20.12e" % self.history[-1])
+            if not ((ediff_rel > conv or rms > conv) and it < maxiter):
+                break
+        self.D, self.F = D, F
+        self.converged = ediff_rel <= conv and rms <= conv
+        self.energy = ehf + self.enuc
+        return self.energy
