@@ -283,11 +283,23 @@ def main():
             "flops_per_quartet": w["flops"], "bytes_per_quartet": 8 * w["blk"] + 8}
     dom = max(per, key=lambda k: per[k]["ms"])
     d = per[dom]
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/traffic.json, written by scripts/ncu_traffic.py on the GPU box); null if the
+    # capture was taken with another launch size
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = tj.get(dom)
+        if t and int(t.get("launch_quartets", 0)) == chunk:
+            traffic = float(t["dram_bytes"])
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": "eri_class_kernel<%s> (%s|%s)" % (dom, dom[:2], dom[2:]),
                 "achieved": d["tflops"], "peak": fp64_peak, "unit": "TFLOP/s", "frac": d["fp64_frac"],
                 "peak_source": "FP64 FMA probe (lb200_fp64_peak_probe) measured in this run; "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "traffic": None, "launch_ms": d["ms"] / nchunks, "share_of_step": d["ms"] / ms_step,
+                "traffic": traffic, "algorithmic_bytes": float((8 * work[list(per).index(dom)]["blk"] + 8) * chunk),
+                "launch_ms": d["ms"] / nchunks, "share_of_step": d["ms"] / ms_step,
                 "hbm": {"achieved": d["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": d["hbm_frac"],
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback"}}
 

@@ -1,6 +1,8 @@
 // Context, basis and shell-pair objects of the C ABI, and the batched ERI entry point.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <limits>
 
 #include "internal.h"
@@ -128,6 +130,12 @@ int lb200_context_destroy(lb200_context* ctx) {
   cudaFree(ctx->d_sph_col);
   cudaFree(ctx->d_sph_val);
   cudaFree(ctx->d_sph_base);
+  for (int i = 0; i < 5; ++i) cudaFree(ctx->d_scratch[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
+    if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return LB200_OK;
@@ -351,6 +359,7 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
       }
     fac_off += (size_t)np1 * np2;
     P->prim_off[i + 1] = (int)P->prim.size();
+    d.max_nprim = std::max(d.max_nprim, P->prim_off[i + 1] - P->prim_off[i]);
   }
   // one device allocation: prim | AB | schwarz | prim_off | shell | bf | gidx
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -426,6 +435,9 @@ int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket
   p.ntasks_dev = nullptr;
   p.ntasks = (unsigned)ntasks;
   p.swap_tasks = pl.swap ? 1 : 0;
+  // LB200_NO_PRIM_KERNEL=1 forces the general (contraction-loop) kernel, for A/B timing
+  static const bool no_prim = getenv("LB200_NO_PRIM_KERNEL") != nullptr;
+  p.uncontracted = (!no_prim && p.bra.max_nprim <= 1 && p.ket.max_nprim <= 1) ? 1 : 0;
   p.boys = ctx->d_boys;
   p.screening = screening;
   if (precision > 0.) {  // Engine::set_precision, engine.h:809-826
@@ -515,16 +527,29 @@ int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pair
   if (chunk > ntasks) chunk = ntasks;
   const bool direct = out_on_device && !need_tform;
   int rc = LB200_OK;
+  // device scratch lives in the context and only grows: no cudaMalloc / cudaFree (= device
+  // synchronisation) per call
+  auto scratch = [&](int slot, size_t bytes, void** out_ptr) -> int {
+    if (ctx->scratch_bytes[slot] < bytes) {
+      cudaStreamSynchronize(ctx->stream);
+      if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+      cudaFree(ctx->d_scratch[slot]);
+      ctx->d_scratch[slot] = nullptr;
+      ctx->scratch_bytes[slot] = 0;
+      int r = check_cuda(ctx, cudaMalloc(&ctx->d_scratch[slot], bytes), "cudaMalloc(scratch)");
+      if (r) return r;
+      ctx->scratch_bytes[slot] = bytes;
+    }
+    *out_ptr = ctx->d_scratch[slot];
+    return LB200_OK;
+  };
   int2* d_tasks = nullptr;
   double* d_cart[2] = {nullptr, nullptr};
   double* d_pure[2] = {nullptr, nullptr};
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   if (tasks_on_device) {
     d_tasks = reinterpret_cast<int2*>(const_cast<int*>(tasks));
   } else {
-    if ((rc = check_cuda(ctx, cudaMalloc(&d_tasks, ntasks * sizeof(int2)), "cudaMalloc(tasks)")))
-      return rc;
+    if ((rc = scratch(0, ntasks * sizeof(int2), reinterpret_cast<void**>(&d_tasks)))) return rc;
     cudaMemcpyAsync(d_tasks, tasks, ntasks * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
   }
   if (direct) {
@@ -532,17 +557,28 @@ int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pair
   } else {
     const int nbuf = (!out_on_device && ntasks > chunk) ? 2 : 1;
     for (int b = 0; b < nbuf && !rc; ++b) {
-      rc = check_cuda(ctx, cudaMalloc(&d_cart[b], chunk * ncart_blk * 8), "cudaMalloc(chunk)");
+      rc = scratch(1 + b, chunk * ncart_blk * 8, reinterpret_cast<void**>(&d_cart[b]));
       if (!rc && need_tform && !out_on_device)
-        rc = check_cuda(ctx, cudaMalloc(&d_pure[b], chunk * nout_blk * 8), "cudaMalloc(chunk)");
-      cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming);
+        rc = scratch(3 + b, chunk * nout_blk * 8, reinterpret_cast<void**>(&d_pure[b]));
     }
-    if (!rc && !out_on_device) cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+    cudaStream_t copy_stream = nullptr;
+    if (!rc && !out_on_device) {
+      if (!ctx->copy_stream) {
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+        for (int b = 0; b < 2; ++b) {
+          cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming);
+          cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming);
+        }
+      }
+      copy_stream = ctx->copy_stream;
+    }
     int b = 0;
+    bool used[2] = {false, false};
     for (long long t0 = 0; t0 < ntasks && !rc; t0 += chunk, b = (b + 1) % nbuf) {
       const long long nt = std::min(chunk, ntasks - t0);
-      if (copy_stream) cudaStreamWaitEvent(ctx->stream, ev_free[b], 0);  // D2H of this buffer done
+      // D2H of this buffer's previous chunk done (events of earlier calls are complete: every
+      // host-output call ends with a copy-stream synchronisation)
+      if (copy_stream && used[b]) cudaStreamWaitEvent(ctx->stream, ctx->ev_free[b], 0);
       rc = run_store(ctx, bra, ket, nt, d_tasks + t0, screening, precision, d_cart[b]);
       if (rc) break;
       const double* src = d_cart[b];
@@ -554,29 +590,20 @@ int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pair
         src = dst;
       }
       if (!out_on_device) {
-        cudaEventRecord(ev_done[b], ctx->stream);
-        cudaStreamWaitEvent(copy_stream, ev_done[b], 0);
+        cudaEventRecord(ctx->ev_done[b], ctx->stream);
+        cudaStreamWaitEvent(copy_stream, ctx->ev_done[b], 0);
         cudaMemcpyAsync(out + t0 * nout_blk, src, nt * nout_blk * 8, cudaMemcpyDeviceToHost,
                         copy_stream);
-        cudaEventRecord(ev_free[b], copy_stream);
+        cudaEventRecord(ctx->ev_free[b], copy_stream);
+        used[b] = true;
       }
     }
-    if (copy_stream) {
-      cudaStreamSynchronize(copy_stream);
-      cudaStreamDestroy(copy_stream);
-    }
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
   }
   if (!rc && (!out_on_device || !tasks_on_device))
     rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "eri_batch");
   else if (!rc)
     rc = check_cuda(ctx, cudaGetLastError(), "eri_batch");
-  for (int b = 0; b < 2; ++b) {
-    cudaFree(d_cart[b]);
-    cudaFree(d_pure[b]);
-    if (ev_done[b]) cudaEventDestroy(ev_done[b]);
-    if (ev_free[b]) cudaEventDestroy(ev_free[b]);
-  }
-  if (!tasks_on_device) cudaFree(d_tasks);
   return rc;
 }
 

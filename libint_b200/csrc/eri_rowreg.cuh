@@ -100,7 +100,9 @@ struct RowMeta {   // per lane, fixed for the whole kernel
   double q[3];     // x,y,z quantum numbers of the row
 };
 
-template <class K, int F, class P1, class P2>
+// ACCUM: targets are added to the contraction accumulators (general kernel) or assigned
+// (uncontracted kernel, eri_rowreg_prim.cuh)
+template <class K, int F, bool ACCUM = true, class P1, class P2>
 __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p1, const P2& p2,
                                                const double (&QC)[3], const double (&WQ)[3],
                                                const double (&koo2e)[6], double roe,
@@ -126,7 +128,10 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
       if constexpr (F < K::FMAX && m >= 1 && K::EMAX > 0) {
         if (rmeta.row < K::NECX) Xq[K::xslot(F, j, m) * K::NECX + rmeta.row] = v;
       }
-      if constexpr (m == 0 && F >= K::LCv) acc[nc_upto(F - 1) - K::F0 + j] += v;
+      if constexpr (m == 0 && F >= K::LCv) {
+        if constexpr (ACCUM) acc[nc_upto(F - 1) - K::F0 + j] += v;
+        else acc[nc_upto(F - 1) - K::F0 + j] = v;
+      }
     });
   });
 }

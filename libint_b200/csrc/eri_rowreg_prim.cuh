@@ -1,0 +1,417 @@
+// Uncontracted ("primitive") specialization of the row-register class kernel (eri_rowreg.cuh)
+// with a software pipeline across quartets.
+//
+// libint generates separate code for uncontracted and contracted shell sets
+// (LIBINT_CONTRACTED_INTS, src/bin/libint/dg.cc:1128-1188: the contraction loop is emitted only
+// for contracted targets); this is the same split for the GPU path: when every shell pair of
+// both pair blocks holds at most one primitive pair there is no K loop, no accumulator set and
+// no per-iteration on/off scaffolding, and -- because one round is one primitive quartet -- the
+// dependent global-memory chain  task -> primitive offsets -> pair records -> Boys table  of
+// round r+1 can be issued while round r computes:
+//
+//   round r   top        offsets(r+1) <- prim_off[task(r+1)],  task(r+2) <- tasks[]   (registers)
+//             VRR        prerequisites + F_m from stage[r&1] (shared, broadcast reads)
+//             mid-VRR    cp.async pair records, A-B, C-D of round r+1 -> stage[(r+1)&1]
+//             ket HRR, transpose to (quartet, cd) lanes
+//             Boys lanes wait for the records, form T / pfac / 1/(zeta+eta) / rho of round r+1,
+//                        publish them and touch their Boys-table row (L1/L2 prefetch by load)
+//             bra HRR, copy-out
+//             Boys lanes evaluate F_m(T)*pfac of round r+1 -> stage[(r+1)&1]
+//
+// so the only exposed memory latency is the first round of a group.  Everything else (row /
+// register-pyramid layout, recurrences, HRR, copy-out) is eri_rowreg.cuh's.
+#pragma once
+#include "eri_rowreg.cuh"
+
+namespace lb200 {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <int LA, int LB, int LC, int LD>
+struct RRP : RRK<LA, LB, LC, LD> {
+  using B = RRK<LA, LB, LC, LD>;
+  // pipeline stage (doubles): bra record 12 | ket record 12 | A-B 3 | C-D 3 | prep 4 | F_m
+  static constexpr int S_BP = 0, S_KP = 12, S_AB = 24, S_CD = 27, S_PREP = 30, S_F = 34;
+  static constexpr int PSTAGE = (S_F + B::L + 1 + 1) & ~1;
+  static constexpr int PIPE = 2 * PSTAGE;
+  // phase areas behind the pipeline stages
+  static constexpr int OFF_X = PIPE;
+  static constexpr int VRR_DOUBLES = OFF_X + (B::EMAX > 0 ? B::XSLOTS * B::NECX : 0);
+  static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
+  static constexpr int OFF_B2 = OFF_FIN + B::NAB * B::CS;    // row -> column transpose buffer
+  static constexpr int P2_DOUBLES = OFF_B2 + (LB > 0 ? B::NCD * B::RTP : 0);
+  static constexpr int QSIZE = (cmax(VRR_DOUBLES, P2_DOUBLES) + 1) & ~1;
+#ifndef LB200_PRIM_MINB_HI
+#define LB200_PRIM_MINB_HI 3
+#endif
+#ifndef LB200_PRIM_MINB_MID
+#define LB200_PRIM_MINB_MID 4
+#endif
+#ifndef LB200_PRIM_MINB_LO
+#define LB200_PRIM_MINB_LO 5
+#endif
+  static constexpr int MINB =
+      B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);
+};
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(RRP<LA, LB, LC, LD>::THREADS, RRP<LA, LB, LC, LD>::MINB)
+eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
+  using K = RRP<LA, LB, LC, LD>;
+  constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
+  constexpr int QSIZE = K::QSIZE, PSTAGE = K::PSTAGE;
+  constexpr bool WL = K::WL;
+  constexpr int GROUP = K::GROUP, QPG = K::QPG, NG = K::NG;
+  static_assert(NEC > 1, "thread-per-quartet classes use the general kernel");
+  static_assert(FMAX <= 6, "register pyramid is written for LC+LD <= 6");
+
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int g = WL ? tid >> 5 : 0;
+  const int gl = WL ? tid & 31 : tid;
+  const int qg = gl / NEC;
+  const bool lane_on = qg < QPG;
+  const int q = g * QPG + qg;
+  auto sync = [] {
+    if constexpr (WL) __syncwarp(); else __syncthreads();
+  };
+  RowMeta rmeta;
+  rmeta.row = lane_on ? gl - qg * NEC : NEC;
+  {
+    const RowInfo ri = rows[rmeta.row];
+    rmeta.e = ri.e;
+    for (int d = 0; d < 3; ++d) {
+      rmeta.rm[d] = ri.rm[d];
+      rmeta.q[d] = (double)ri.q[d];
+    }
+  }
+  int cdir_[EMAX > 0 ? EMAX : 1];
+  double ccnt_[EMAX > 0 ? EMAX : 1];
+  if constexpr (EMAX > 0) {
+    const int qx = (int)rmeta.q[0], qy = (int)rmeta.q[1];
+    static_for<EMAX>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      const int s = k - (EMAX - rmeta.e);
+      int d = -1, c = 0;
+      if (s >= 0) {
+        if (s < qx) { d = 0; c = s; }
+        else if (s < qx + qy) { d = 1; c = s - qx; }
+        else { d = 2; c = s - qx - qy; }
+      }
+      cdir_[k] = d;
+      ccnt_[k] = (double)c;
+    });
+  }
+  double* const Q = smem + (size_t)(lane_on ? q : 0) * QSIZE;
+  const bool boys_lane = lane_on && rmeta.row <= L;
+
+  const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
+  const unsigned stride = gridDim.x * NG * QPG;
+  unsigned base = (blockIdx.x * NG + g) * QPG;
+  if (base >= ntasks) return;   // whole group idle (groups never share barriers when WL;
+                                // for the CTA-wide group the condition is CTA-uniform)
+
+  // ---- pipeline helpers ---------------------------------------------------------------
+  // primitive offsets of a task: (first bra primitive, first ket primitive), -1 if the task is
+  // out of range or either pair kept no primitive
+  auto load_task = [&](unsigned b) -> int2 {
+    const unsigned t = b + qg;
+    if (!lane_on || t >= ntasks) return make_int2(-1, -1);
+    const int2 tk = p.tasks[t];
+    return p.swap_tasks ? make_int2(tk.y, tk.x) : tk;
+  };
+  struct Off { int pb, pk, ib, ik; };   // ib < 0: no task; pb < 0: a pair kept no primitive
+  auto load_off = [&](int2 tk) -> Off {
+    Off o{-1, -1, -1, -1};
+    if (tk.x < 0) return o;
+    const int pb0 = p.bra.prim_off[tk.x], pb1 = p.bra.prim_off[tk.x + 1];
+    const int pk0 = p.ket.prim_off[tk.y], pk1 = p.ket.prim_off[tk.y + 1];
+    o.ib = tk.x; o.ik = tk.y;
+    if (pb1 > pb0 && pk1 > pk0) { o.pb = pb0; o.pk = pk0; }
+    return o;
+  };
+  // 18 chunks per quartet: 6 + 6 sixteen-byte pieces of the two records, 3 + 3 doubles of A-B, C-D
+  // (A-B / C-D for every real task: the HRR of an all-screened quartet must see finite numbers)
+  auto issue_records = [&](const Off& o, double* S) {
+    if (lane_on && o.ib >= 0) {
+      const char* gb = reinterpret_cast<const char*>(p.bra.prim + (o.pb < 0 ? 0 : o.pb));
+      const char* gk = reinterpret_cast<const char*>(p.ket.prim + (o.pk < 0 ? 0 : o.pk));
+      for (int c = rmeta.row; c < 18; c += NEC) {
+        if (c < 12) {
+          if (o.pb < 0) continue;
+          if (c < 6) cp_async16(S + K::S_BP + 2 * c, gb + 16 * c);
+          else cp_async16(S + K::S_KP + 2 * (c - 6), gk + 16 * (c - 6));
+        } else if (c < 15) {
+          cp_async8(S + K::S_AB + (c - 12), p.bra.AB + 3 * o.ib + (c - 12));
+        } else {
+          cp_async8(S + K::S_CD + (c - 15), p.ket.AB + 3 * o.ik + (c - 15));
+        }
+      }
+    }
+  };
+  // Boys lanes, first half: T, pfac (registers), 1/(zeta+eta), rho, on (published by row 0)
+  struct BoysState { double T, pfac; bool on; };
+  auto boys_prepare = [&](const Off& o, double* S) -> BoysState {
+    BoysState b{0.0, 0.0, false};
+    if (!boys_lane) return b;
+    bool on = o.pb >= 0;
+    double oogpq = 0.0, rho = 0.0;
+    if (on) {
+      const double lnb = S[K::S_BP + 9], lnk = S[K::S_KP + 9];
+      on = lnb + lnk > p.ln_precision;   // engine.impl.h:1313-1314
+    }
+    if (on) {
+      const double PQx = S[K::S_BP + 0] - S[K::S_KP + 0], PQy = S[K::S_BP + 1] - S[K::S_KP + 1],
+                   PQz = S[K::S_BP + 2] - S[K::S_KP + 2];
+      const double PQ2 = PQx * PQx + PQy * PQy + PQz * PQz;
+      const double gb = S[K::S_BP + 7], gk = S[K::S_KP + 7];
+      const double gpq = gb + gk;
+      oogpq = 1.0 / gpq;
+      b.pfac = S[K::S_BP + 6] * S[K::S_KP + 6] * sqrt(gpq) * oogpq;
+      if (p.screening & (kScreenOriginal | kScreenConservative)) {  // engine.impl.h:1371-1386
+        double est = fabs(b.pfac);
+        if (p.screening == kScreenConservative)
+          est *= fmax(1.0, S[K::S_BP + 10] * S[K::S_KP + 10]);  // npbra * npket = 1
+        if (est < p.precision) on = false;
+      }
+      rho = gb * gk * oogpq;
+      b.T = PQ2 * rho;
+    }
+    b.on = on;
+    if (rmeta.row == 0) {
+      S[K::S_PREP + 0] = oogpq;
+      S[K::S_PREP + 1] = rho;
+      S[K::S_PREP + 2] = on ? 1.0 : 0.0;
+    }
+    return b;
+  };
+  // touch this lane's first Boys-table row so that boys_finish finds it in L1
+  auto boys_touch = [&](const BoysState& b) -> double {
+    if (!boys_lane || !b.on || b.T > kBoysTmax) return 0.0;
+    int iv = (int)(b.T * 7.0);
+    iv = iv > kBoysNInt - 1 ? kBoysNInt - 1 : iv;
+    const double* d = p.boys + ((size_t)iv * (kBoysTableMmax + 1) + rmeta.row) * 8;
+    return __ldg(d) + __ldg(d + 4);
+  };
+  auto boys_finish = [&](const BoysState& b, double* S) {
+    if (boys_lane)
+      for (int m = rmeta.row; m <= L; m += NEC)
+        S[K::S_F + m] = b.on ? boys_value(p.boys, b.T, m) * b.pfac : 0.0;
+  };
+
+  // ---- prologue: round 0 of this group, unpipelined ---------------------------------------
+  int2 tk_next;
+  {
+    const int2 tk0 = load_task(base);
+    tk_next = load_task(base + stride);
+    const Off o0 = load_off(tk0);
+    issue_records(o0, Q);
+    cp_async_wait_all();
+    sync();
+    const BoysState b0 = boys_prepare(o0, Q);
+    boys_finish(b0, Q);
+  }
+
+  for (int round = 0; base < ntasks; base += stride, ++round) {
+    double* const S = Q + (round & 1) * PSTAGE;          // this round's stage
+    double* const SN = Q + ((round + 1) & 1) * PSTAGE;   // next round's stage
+    const bool more = base + stride < ntasks;            // group-uniform
+    // ---- top: next round's offsets, the task after that (consumed later in this round) ----
+    const Off onext = more ? load_off(tk_next) : Off{-1, -1, -1, -1};
+    const int2 tk_next2 = (more && base + 2 * stride < ntasks) ? load_task(base + 2 * stride)
+                                                                : make_int2(-1, -1);
+    sync();   // stage S complete (prologue / previous round); previous phase 2 finished
+
+    // ---- prerequisites from the stage (engine.impl.h:1331-1367,1389-1392,1602-1641) --------
+    const bool on = S[K::S_PREP + 2] != 0.0;
+    double PA[3], WP[3], QC[3], WQ[3], oo2z, roz, koo2e[6], roe, ce[3];
+    {
+      const double oogpq = S[K::S_PREP + 0], rho = S[K::S_PREP + 1];
+      const double gb = S[K::S_BP + 7], gk = S[K::S_KP + 7];
+      const double oogb = S[K::S_BP + 8], oogk = S[K::S_KP + 8];
+      const double gp = oogpq * gb, gq = oogpq * gk;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double Pb = S[K::S_BP + d], Pk = S[K::S_KP + d];
+        const double W = gp * Pb + gq * Pk;
+        WP[d] = W - Pb;
+        WQ[d] = W - Pk;
+        PA[d] = S[K::S_BP + 3 + d];
+        QC[d] = S[K::S_KP + 3 + d];
+      }
+      oo2z = 0.5 * oogb;
+      roz = rho * oogb;
+      const double oo2e = 0.5 * oogk;
+      koo2e[0] = 0.0; koo2e[1] = oo2e; koo2e[2] = 2.0 * oo2e; koo2e[3] = 3.0 * oo2e;
+      koo2e[4] = 4.0 * oo2e; koo2e[5] = 5.0 * oo2e;
+      roe = rho * oogk;
+      const double oo2ze = 0.5 * oogpq;
+      ce[0] = rmeta.q[0] * oo2ze; ce[1] = rmeta.q[1] * oo2ze; ce[2] = rmeta.q[2] * oo2ze;
+    }
+    double CD[3] = {S[K::S_CD], S[K::S_CD + 1], S[K::S_CD + 2]};
+    double F[L + 1];
+    static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] = S[K::S_F + decltype(mc)::value]; });
+
+    // ---- [row 0|00]^(m): private chain (vrr_11_twoprep_11.h:154-222) ----------------------
+    double acc[K::NFT];
+    Lvl<FMAX, 0> l0;
+    {
+      double cur[L + 1], prv[L + 1];
+      static_for<L + 1>([&](auto mc) {
+        cur[decltype(mc)::value] = F[decltype(mc)::value];
+        prv[decltype(mc)::value] = 0.0;
+      });
+      static_for<EMAX>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const int d = cdir_[k];
+        const double pa = d < 0 ? 1.0 : sel3(d, PA[0], PA[1], PA[2]);
+        const double wp = d < 0 ? 0.0 : sel3(d, WP[0], WP[1], WP[2]);
+        const double c = ccnt_[k] * oo2z;
+        static_for<L - k>([&](auto mc) {
+          constexpr int m = decltype(mc)::value;
+          const double nv = pa * cur[m] + wp * cur[m + 1] + c * (prv[m] - roz * prv[m + 1]);
+          prv[m] = cur[m];
+          cur[m] = nv;
+        });
+      });
+      static_for<FMAX + 1>([&](auto mc) { l0.v[decltype(mc)::value] = cur[decltype(mc)::value]; });
+      if (lane_on && rmeta.row < NECX)
+        static_for<FMAX>([&](auto mc) {
+          constexpr int m = decltype(mc)::value + 1;
+          Q[K::OFF_X + K::xslot(0, 0, m) * NECX + rmeta.row] = l0.v[m];
+        });
+    }
+    if constexpr (LC == 0) acc[0] = l0.v[0];
+
+    // next round's records: the stage SN was last read before this round's top barrier
+    issue_records(onext, SN);
+
+    // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -----------------------
+    double* Xq = Q + K::OFF_X;
+    if constexpr (FMAX >= 1) {
+      sync();
+      Lvl<FMAX, 1> l1;
+      rr_build_level<K, 1, false>(l1, l0, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+      if constexpr (FMAX >= 2) {
+        sync();
+        Lvl<FMAX, 2> l2;
+        rr_build_level<K, 2, false>(l2, l1, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+        if constexpr (FMAX >= 3) {
+          sync();
+          Lvl<FMAX, 3> l3;
+          rr_build_level<K, 3, false>(l3, l2, l1, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+          if constexpr (FMAX >= 4) {
+            sync();
+            Lvl<FMAX, 4> l4;
+            rr_build_level<K, 4, false>(l4, l3, l2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+            if constexpr (FMAX >= 5) {
+              sync();
+              Lvl<FMAX, 5> l5;
+              rr_build_level<K, 5, false>(l5, l4, l3, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+              if constexpr (FMAX >= 6) {
+                sync();
+                Lvl<FMAX, 6> l6;
+                rr_build_level<K, 6, false>(l6, l5, l4, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+              }
+            }
+          }
+        }
+      }
+    }
+
+    // ---- ket HRR in registers: (row 0|c d) from (row 0|f 0), hrr.h:324 ---------------------
+    double H[K::NCD];
+    rr_hrr_regs<LC, LD>(acc, CD, H);
+    if (!on) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
+
+    const unsigned task = base + qg;
+    const bool valid = lane_on && task < ntasks;
+    sync();   // last cross-term reads done: the phase-2 areas alias the cross-term area
+    constexpr int TBOFF = K::OFF_B2;
+    if constexpr (LB > 0) {
+      if (valid && rmeta.row >= K::ROW0)
+        static_for<K::NCD>([&](auto ic) {
+          Q[TBOFF + decltype(ic)::value * K::RTP + (rmeta.row - K::ROW0)] = H[decltype(ic)::value];
+        });
+    } else {
+      if (valid && rmeta.row >= K::ROW0)
+        static_for<K::NCD>([&](auto ic) {
+          Q[K::OFF_FIN + (rmeta.row - K::ROW0) * K::CS + decltype(ic)::value] = H[decltype(ic)::value];
+        });
+    }
+    cp_async_wait_all();   // own copies of the next round's records have landed ...
+    sync();                // ... and everybody else's; transposed rows visible
+
+    // ---- next round, Boys lanes: T, pfac, 1/(zeta+eta), rho; touch the table row ----------
+    const BoysState bn = boys_prepare(onext, SN);
+    const double touched = boys_touch(bn);
+
+    if constexpr (LB > 0) {
+      // ---- bra HRR in registers: (a b|c d) from (e 0|c d), hrr.h:246 -----------------------
+      for (int item = gl; item < QPG * K::NCD; item += GROUP) {
+        const int q2 = item / K::NCD, cd = item - q2 * K::NCD;
+        if (base + q2 >= ntasks) continue;
+        double* Q2 = smem + (size_t)(g * QPG + q2) * QSIZE;
+        const double* S2 = Q2 + (round & 1) * PSTAGE;
+        const double ABv[3] = {S2[K::S_AB], S2[K::S_AB + 1], S2[K::S_AB + 2]};
+        double colin[K::NRT];
+        static_for<K::NRT>([&](auto rc) {
+          colin[decltype(rc)::value] = Q2[TBOFF + cd * K::RTP + decltype(rc)::value];
+        });
+        double O[K::NAB];
+        rr_hrr_regs<LA, LB>(colin, ABv, O);
+        if (!p.transpose_out) {
+          double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
+          static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
+        } else {
+          double* fin = Q2 + K::OFF_FIN;
+          static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
+        }
+      }
+      if (p.transpose_out) sync();
+    }
+    {
+      // ---- coalesced copy-out (see eri_rowreg.cuh) ----------------------------------------
+      constexpr int BLK = K::NAB * K::NCD;
+      const unsigned left = ntasks - base;
+      const int nvalid = left < (unsigned)QPG ? (int)left : QPG;
+      double* __restrict__ o = p.out + (size_t)base * BLK;
+      if (!p.transpose_out) {
+        if constexpr (LB == 0) {
+          for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
+            const int q2 = idx / BLK, i = idx - q2 * BLK;
+            const int ab = i / K::NCD, cd = i - ab * K::NCD;
+            o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN + ab * K::CS + cd];
+          }
+        }
+      } else {
+        for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
+          const int q2 = idx / BLK, i = idx - q2 * BLK;
+          const int cd = i / K::NAB, ab = i - cd * K::NAB;
+          o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN + ab * K::CS + cd];
+        }
+      }
+    }
+    // ---- next round, Boys lanes: F_m(T) * pfac ---------------------------------------------
+    {
+      BoysState b2 = bn;
+      // keep the touch alive without changing any value: (touched != touched) is false for
+      // every finite table entry
+      if (touched != touched) b2.pfac = touched;
+      boys_finish(b2, SN);
+    }
+    tk_next = tk_next2;
+  }
+}
+
+}  // namespace lb200

@@ -21,6 +21,12 @@ struct lb200_context {
   double* d_sph_val = nullptr;
   int* d_sph_base = nullptr;     // [(kMaxShellL+1)] offset of each l into col/val
   long long launches = 0;
+  // scratch of the host-buffer lb200_eri_batch path, kept between calls (grown on demand):
+  // task list, two Cartesian / two transformed chunk buffers, copy stream and its events
+  void* d_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   mutable std::string err;
 };
 

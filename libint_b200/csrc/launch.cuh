@@ -4,7 +4,7 @@
 // eri_rowreg_kernel (eri_rowreg.cuh) with rows = the smaller pair and the other pair unrolled in
 // registers whenever X has l1+l2 <= 4; for the (fd|, (ff| bras the roles are exchanged.
 #pragma once
-#include "eri_rowreg.cuh"
+#include "eri_rowreg_prim.cuh"
 
 namespace lb200 {
 
@@ -36,6 +36,33 @@ cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
   return cudaGetLastError();
 }
 
+// uncontracted pair blocks, store mode, more than one row per quartet: pipelined kernel
+template <int LA, int LB, int LC, int LD>
+cudaError_t launch_rowreg_prim(const EriParams& p, const RowInfo* rows, int num_sms,
+                               cudaStream_t stream) {
+  using K = RRP<LA, LB, LC, LD>;
+  constexpr int SMEM = K::QPC * K::QSIZE * 8;
+  static_assert(SMEM <= kSmemLimit, "pipelined row-register kernel exceeds shared memory");
+  auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD>;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (err != cudaSuccess) return err;
+    int nb = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::THREADS, SMEM);
+    if (err != cudaSuccess) return err;
+    ctas_per_sm = nb < 1 ? 1 : nb;
+  }
+  long long grid = (long long)num_sms * ctas_per_sm;
+  if (!p.ntasks_dev) {
+    const long long need = ((long long)p.ntasks + K::QPC - 1) / K::QPC;
+    if (need < grid) grid = need;
+  }
+  if (grid < 1) return cudaSuccess;
+  kern<<<(unsigned)grid, K::THREADS, SMEM, stream>>>(p, rows);
+  return cudaGetLastError();
+}
+
 template <int LA, int LB, int LC, int LD, int MODE>
 cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
                          cudaStream_t stream) {
@@ -46,10 +73,16 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
     q.ket = p.bra;
     q.swap_tasks = p.swap_tasks ^ 1;
     q.transpose_out = p.transpose_out ^ 1;
+    if constexpr (MODE != kModeFock && RR<LC, LD, LA, LB>::NEC > 1) {
+      if (p.uncontracted) return launch_rowreg_prim<LC, LD, LA, LB>(q, rows, num_sms, stream);
+    }
     return launch_rowreg<LC, LD, LA, LB, MODE>(q, rows, num_sms, stream);
   } else {
     // (fd|, (ff| bras: rows = the big pair, the other pair unrolled (up to l1+l2 = 6; beyond 4
     // the register pyramid spills to local memory -- these classes are rare)
+    if constexpr (MODE != kModeFock) {
+      if (p.uncontracted) return launch_rowreg_prim<LA, LB, LC, LD>(p, rows, num_sms, stream);
+    }
     return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
   }
 }

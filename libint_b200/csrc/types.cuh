@@ -36,6 +36,7 @@ struct PairBlock {
   const int* bf;           // [npair][2]  first basis function of each shell
   const double* schwarz;   // [npair]     sqrt(max|(ab|ab)|)          (Fock build only)
   const int* gidx;         // [npair]     canonical pair index s1(s1+1)/2+s2 (Fock build only)
+  int max_nprim;           // largest number of primitive pairs kept by any pair of the block
 };
 
 enum ScreeningMethod : int {  // values follow shell.h:1041-1059
@@ -53,6 +54,7 @@ struct EriParams {
   const unsigned* ntasks_dev;  // if non-null, task count is read from device memory
   unsigned ntasks;
   int swap_tasks;             // 1: tasks are (ket pair, bra pair) in kernel orientation
+  int uncontracted;           // 1: no pair of either block holds more than one primitive pair
   unsigned* work_counter;    // dynamic scheduling counter (zeroed by host)
   const double* boys;        // [kBoysNInt][kBoysTableMmax+1][8]
   // primitive screening (engine.impl.h:1313-1314,1371-1386)

@@ -132,4 +132,4 @@ def test_gpu_scf_config1_h2o_ccpvdz(ctx, oracle):
     assert len(s_gpu.history) == len(s_cpu.history)
     for a, c in zip(s_gpu.history, s_cpu.history):
         assert abs(a[1] - c[1]) < 1e-9
-    assert -76.03 < e_gpu < -76.02   # RHF/cc-pVDZ water
+    assert -76.0 < e_gpu < -75.98   # RHF/cc-pVDZ at h2o.xyz's stretched geometry (r_OH = 1.10 A)
