@@ -63,10 +63,23 @@ struct RR {
   static constexpr int OFF_B2 = HDR + NAB * CS;
   static constexpr int FOCK_DOUBLES = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);
   static constexpr int STORE_DOUBLES = OFF_B2 + (LB > 0 ? NCD * RTP : 0);
+  // Stride between the regions of consecutive quartets.  The lanes of a warp that belong to
+  // different quartets touch the same offset of their regions at the same time, so the stride
+  // decides the bank pattern: with stride = NEC (mod 16 eight-byte banks) a half-warp's
+  // quartets tile the banks (row-indexed accesses) or land in distinct banks (broadcast
+  // accesses); a stride that is a multiple of 16 would serialise every access QPG ways.
+  static constexpr int pad_stride(int s) {
+    s = (s + 1) & ~1;
+    if (NEC > 1 && NEC <= 16) {
+      const int want = (NEC + (NEC & 1)) % 16;
+      while (s % 16 != want) s += 2;
+    }
+    return s;
+  }
   static constexpr int qsize(bool fock) {
     int s = cmax(PRIM_DOUBLES, STORE_DOUBLES);
     if (fock) s = cmax(s, FOCK_DOUBLES);
-    return (s + 1) & ~1;
+    return pad_stride(s);
   }
   static constexpr int threads() {
     if (NEC <= 32) return 128;

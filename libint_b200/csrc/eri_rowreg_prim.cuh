@@ -50,15 +50,15 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
   static constexpr int OFF_B2 = OFF_FIN + B::NAB * B::CS;    // row -> column transpose buffer
   static constexpr int P2_DOUBLES = OFF_B2 + (LB > 0 ? B::NCD * B::RTP : 0);
-  static constexpr int QSIZE = (cmax(VRR_DOUBLES, P2_DOUBLES) + 1) & ~1;
+  static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
 #define LB200_PRIM_MINB_HI 3
 #endif
 #ifndef LB200_PRIM_MINB_MID
-#define LB200_PRIM_MINB_MID 4
+#define LB200_PRIM_MINB_MID 5
 #endif
 #ifndef LB200_PRIM_MINB_LO
-#define LB200_PRIM_MINB_LO 5
+#define LB200_PRIM_MINB_LO 6
 #endif
   static constexpr int MINB =
       B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);

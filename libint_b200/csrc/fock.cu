@@ -280,13 +280,33 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
   f->obs = *obs;
   const int ns = obs->nshell;
   f->K.assign((size_t)ns * ns, 0.0);
-  // group by class, first shell = higher AM
-  std::map<std::array<int, 4>, std::pair<std::vector<int>, std::vector<int>>> groups;
+  // group by class (first shell = higher AM) and by contraction degree: the quartets of one
+  // launch advance through their primitive loops in lockstep (per warp / per CTA), so pairs
+  // with very different numbers of primitive pairs must not share a block.  Bucket upper
+  // bounds on nprim(a)*nprim(b); LB200_FOCK_BUCKETS="1,6" style override for experiments.
+  std::vector<int> bounds = {1, 6};
+  if (const char* e = std::getenv("LB200_FOCK_BUCKETS")) {
+    bounds.clear();
+    for (const char* q = e; *q;) {
+      char* end = nullptr;
+      const long v = std::strtol(q, &end, 10);
+      if (end == q) break;
+      if (v > 0) bounds.push_back((int)v);
+      q = (*end == ',') ? end + 1 : end;
+    }
+  }
+  auto bucket_of = [&](int npp) {
+    int k = 0;
+    while (k < (int)bounds.size() && npp > bounds[k]) ++k;
+    return k;
+  };
+  std::map<std::array<int, 5>, std::pair<std::vector<int>, std::vector<int>>> groups;
   for (long long i = 0; i < npair; ++i) {
     int a = s1[i], b = s2[i];
     if (a < 0 || b < 0 || a >= ns || b >= ns) { delete f; return LB200_ERR_INVALID; }
     if (obs->l[a] < obs->l[b]) std::swap(a, b);
-    auto& g = groups[{obs->l[a], obs->l[b], obs->pure[a], obs->pure[b]}];
+    auto& g = groups[{obs->l[a], obs->l[b], obs->pure[a], obs->pure[b],
+                      bucket_of(obs->nprim[a] * obs->nprim[b])}];
     g.first.push_back(a);
     g.second.push_back(b);
   }
@@ -325,7 +345,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
   }
   if (rc) { lb200_fock_destroy(f); return rc; }
   // kernel orientation wants bra key >= ket key: keep classes sorted by key
-  std::sort(f->classes.begin(), f->classes.end(), [](const FockClass& x, const FockClass& y) {
+  std::stable_sort(f->classes.begin(), f->classes.end(), [](const FockClass& x, const FockClass& y) {
     return order_key(x.la, x.lb) < order_key(y.la, y.lb);
   });
   std::vector<int> ssz(ns);

@@ -66,6 +66,17 @@ cudaError_t launch_rowreg_prim(const EriParams& p, const RowInfo* rows, int num_
 template <int LA, int LB, int LC, int LD, int MODE>
 cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
                          cudaStream_t stream) {
+  if constexpr (MODE != kModeFock && LA == LC && LB == LD && LA + LB <= 4) {
+    // both pairs of one class: either may be the row side.  Pick the orientation whose output
+    // is in the caller's order, so that the bra-HRR lanes store straight to global memory
+    // instead of going through the transposing copy-out.
+    if (!p.transpose_out) {
+      if constexpr (RR<LA, LB, LC, LD>::NEC > 1) {
+        if (p.uncontracted) return launch_rowreg_prim<LA, LB, LC, LD>(p, rows, num_sms, stream);
+      }
+      return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
+    }
+  }
   if constexpr (LA + LB <= 4) {
     // rows = (LC LD| (the smaller pair), (LA LB) unrolled: the kernel sees bra and ket swapped
     EriParams q = p;
