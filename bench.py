@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--fock-basis", default="def2-tzvp")
     ap.add_argument("--fock-precision", type=float, default=1e-10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-df3c", action="store_true")
+    ap.add_argument("--df3c-carbons", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -334,6 +336,14 @@ def main():
         except capi.Lb200Error as e:
             fock = {"error": str(e)}
 
+    # ---- 3-centre (P|mu nu) class sweep (configs[3]): C40H82, def2-TZVP / def2-universal-JKFIT -
+    df3c = None
+    if not args.no_df3c:
+        try:
+            df3c = run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world)
+        except capi.Lb200Error as e:
+            df3c = {"error": str(e)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -343,7 +353,7 @@ def main():
                        "l2_policy": "outputs (%.1f GB per class) exceed L2; pair tables are L2-resident by design"
                                     % (8 * max_blk * chunk / 1e9)},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "per_class": per, "fock": fock}
+            "per_class": per, "fock": fock, "df3c": df3c}
 
     if rank == 0 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1
@@ -355,6 +365,41 @@ def main():
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world):
+    """every (P|mu nu) shell triplet of an all-trans alkane once (replicated per rank: the tensor
+    shards by DF shell with no collective, SURVEY 8e -- here each rank sweeps the whole list)."""
+    import torch
+    from libint_b200.basis import BasisSet, alkane
+    from libint_b200.df3c import ThreeCenter
+    atoms = alkane(args.df3c_carbons)
+    obs, dfbs = BasisSet("def2-tzvp", atoms), BasisSet("def2-tzvp-jk", atoms)
+    t0 = time.perf_counter()
+    tc = ThreeCenter(ctx, obs, dfbs)
+    setup_s = time.perf_counter() - t0
+    with torch.cuda.stream(stream):
+        tc.sweep(out)
+        barrier()
+        ev = []
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n = tc.sweep(out, events=ev)
+        e1.record(stream)
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    nints = sum(nn * blk for _, nn, blk, _, _ in ev)
+    top = sorted(ev, key=lambda x: -x[3].elapsed_time(x[4]))[:6]
+    return {"workload": "C%dH%d (P|mu nu), obs def2-tzvp (%d shells, %d bf), dfbs def2-tzvp-jk (%d shells, %d bf, "
+                        "max l %d), %d significant orbital pairs" % (args.df3c_carbons, 2 * args.df3c_carbons + 2,
+                                                                      len(obs), obs.nbf, len(dfbs), dfbs.nbf,
+                                                                      dfbs.max_l, tc.npairs),
+            "shell_triplets": n, "classes": len(tc.classes()), "seconds": ms * 1e-3,
+            "triplets_per_s": n / (ms * 1e-3), "cartesian_integrals": nints,
+            "hbm_write_gbs": nints * 8 / (ms * 1e-3) / 1e9, "setup_seconds": setup_s,
+            "slowest_classes": [{"class": "(%d s|%d %d)" % c, "triplets": nn,
+                                 "ns_per_triplet": 1e6 * a.elapsed_time(b) / nn} for c, nn, _, a, b in top]}
 
 
 def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_):
@@ -407,7 +452,34 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
         t = torch.tensor([nquart], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(t)
         nquart = float(t.item())
-    return {"workload": "(H2O)_%d / %s direct Fock (J - K/2), Schwarz x density screened at %g"
+    # CPU side of the same metric: the reference's multithreaded compute_2body_fock pattern
+    # (oracle: reference Engine per thread on the restated kernels) on the box's host cores.  Its
+    # task enumeration alone is O(npair^2) per thread, so it is timed on a bounded sample of the
+    # workload -- an (H2O)_8 sub-cluster of the same lattice and basis -- and the GPU is timed on
+    # that sub-cluster as well.
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        obs8 = BasisSet(args.fock_basis, water_cluster(2, 2, 2))
+        B8 = capi.Basis(ctx, *obs8.flat())
+        f8 = capi.Fock(ctx, B8)
+        C8 = rng.standard_normal((obs8.nbf, max(1, obs8.nbf // 8))) / np.sqrt(obs8.nbf)
+        D8 = C8 @ C8.T
+        f8.build(D8, args.fock_precision)
+        t0 = time.perf_counter()
+        G8, st8 = f8.build(D8, args.fock_precision, stats=True)
+        gpu8_s = st8["ms"] * 1e-3
+        ncores = os.cpu_count() or 1
+        of = po.Fock(po.Shells(*obs8.flat(), raw=False), f8.pair_s1, f8.pair_s2, nthreads=ncores)
+        Gc, stc = of.build(D8, args.fock_precision)
+        err = float(np.max(np.abs(G8 - Gc) - 1e-12 * np.abs(Gc)))
+        cpu = {"value": stc["nquartets"] / stc["seconds"], "unit": "shell quartets/s", "cores": ncores,
+               "kind": "port", "seconds": stc["seconds"],
+               "sample": "(H2O)_8 / %s sub-cluster, full build, %d shell quartets" % (args.fock_basis, int(stc["nquartets"])),
+               "gpu_seconds_same_sample": gpu8_s, "gpu_quartets_per_s_same_sample": st8["nquartets"] / gpu8_s,
+               "max_abs_err_beyond_1e-12_rel": err}
+    return {"cpu_baseline": cpu,
+            "workload": "(H2O)_%d / %s direct Fock (J - K/2), Schwarz x density screened at %g"
                         % (nx * ny * nz, args.fock_basis, args.fock_precision),
             "nshell": len(obs), "nbf": n, "significant_pairs": int(len(f.pair_s1)),
             "shell_quartets": nquart, "seconds": sec, "e2e_seconds": e2e_sec,

@@ -291,7 +291,26 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     __syncthreads();
   }
   int round = 0;
-  for (unsigned base = (blockIdx.x * NG + g) * QPG; base < ntasks; base += gridDim.x * NG * QPG) {
+  // Fock mode: groups pull their next QPG tasks from a device counter (zeroed by the host before
+  // the launch).  The quartets of one launch differ by orders of magnitude in primitive count,
+  // so a static round-robin leaves SMs idle while a few groups finish the heavy ones.
+  // (Splitting one task's primitive loop over several slots was measured too: slower, the
+  // per-task HRR + digestion then runs on a fraction of the lanes.)
+  __shared__ unsigned s_base[2];
+  auto next_base = [&](int r) -> unsigned {
+    if constexpr (!FOCK) {
+      return (unsigned)((blockIdx.x * NG + g) * QPG) + (unsigned)r * (gridDim.x * NG * QPG);
+    } else if constexpr (WL) {
+      unsigned b = 0;
+      if (gl == 0) b = atomicAdd(p.work_counter, (unsigned)QPG);
+      return __shfl_sync(0xffffffffu, b, 0);
+    } else {
+      if (tid == 0) s_base[r & 1] = atomicAdd(p.work_counter, (unsigned)QPG);
+      __syncthreads();
+      return s_base[r & 1];
+    }
+  };
+  for (unsigned base = next_base(0); base < ntasks; base = next_base(round)) {
     const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
     int ib = 0, ik = 0, pb0 = 0, nb = 0, pk0 = 0, nk = 0;

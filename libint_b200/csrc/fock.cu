@@ -354,7 +354,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
   cudaMalloc(&f->d_shellsize, ns * sizeof(int));
   cudaMalloc(&f->d_Dnorm, (size_t)ns * ns * 8);
   cudaMalloc(&f->d_scalar, 8);
-  cudaMalloc(&f->d_count, 4);
+  cudaMalloc(&f->d_count, 8);   // [0] task count, [1] dynamic-scheduling cursor of the class kernel
   cudaMemcpy(f->d_shell2bf, obs->shell2bf.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(f->d_shellsize, ssz.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
   rc = check_cuda(ctx, cudaGetLastError(), "fock_create");
@@ -479,7 +479,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
           sp.rank = rank; sp.nranks = nranks;
           sp.tasks = f->d_tasks; sp.count = f->d_count; sp.cap = (unsigned)cap;
-          cudaMemsetAsync(f->d_count, 0, 4, st);
+          cudaMemsetAsync(f->d_count, 0, 8, st);
           const int wpb = 8;
           const int grid = std::min(ctx->num_sms * 8, (sp.nrow + wpb - 1) / wpb);
           screen_kernel<<<grid, wpb * 32, 0, st>>>(sp);
@@ -487,6 +487,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           EriParams p{};
           p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
           p.tasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
+          p.work_counter = f->d_count + 1;
           p.boys = ctx->d_boys;
           p.screening = kScreenSchwarzInf;
           p.D = f->d_D; p.F = f->d_F; p.nbf = n; p.Dnorm = f->d_Dnorm; p.nshell = ns;

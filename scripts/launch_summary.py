@@ -18,7 +18,7 @@ for r in rows[1:]:
     a[0] += 1
     a[1] += float(r[iv].replace(",", "")) * scale[r[iu]]
 tot = sum(a[1] for a in agg.values())
-store = {n: a for n, a in agg.items() if re.search(r"eri_rowreg_kernel<\d, \d, \d, \d, 0>", n)}
+store = {n: a for n, a in agg.items() if re.search(r"eri_rowreg_kernel<\d, \d, \d, \d, 0>|eri_rowreg_prim_kernel<", n)}
 stot = sum(a[1] for a in store.values())
 print("%d launches captured, %.3f ms device time; store-mode class kernels %.3f ms" % (len(rows) - 1, tot, stot))
 print("%7s %11s %7s %9s  kernel" % ("count", "total ms", "share", "of sweep"))
