@@ -37,7 +37,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-template <int LA, int LB, int LC, int LD>
+// TR: the caller's bra is this kernel's unrolled side, results leave as [cd][ab] through the
+// transposing copy-out.  TR = false with LB > 0 stores straight from the bra-HRR lanes and needs
+// no staging buffer for the final integrals: a third less shared memory, one more CTA per SM.
+template <int LA, int LB, int LC, int LD, bool TR>
 struct RRP : RRK<LA, LB, LC, LD> {
   using B = RRK<LA, LB, LC, LD>;
   // pipeline stage (doubles): bra record 12 | ket record 12 | A-B 3 | C-D 3 | prep 4 | F_m
@@ -48,7 +51,8 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int OFF_X = PIPE;
   static constexpr int VRR_DOUBLES = OFF_X + (B::EMAX > 0 ? B::XSLOTS * B::NECX : 0);
   static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
-  static constexpr int OFF_B2 = OFF_FIN + B::NAB * B::CS;    // row -> column transpose buffer
+  static constexpr bool HAS_FIN = TR || LB == 0;
+  static constexpr int OFF_B2 = OFF_FIN + (HAS_FIN ? B::NAB * B::CS : 0);  // row -> column transpose buffer
   static constexpr int P2_DOUBLES = OFF_B2 + (LB > 0 ? B::NCD * B::RTP : 0);
   static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
@@ -64,10 +68,10 @@ struct RRP : RRK<LA, LB, LC, LD> {
       B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);
 };
 
-template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(RRP<LA, LB, LC, LD>::THREADS, RRP<LA, LB, LC, LD>::MINB)
+template <int LA, int LB, int LC, int LD, bool TR>
+__global__ void __launch_bounds__(RRP<LA, LB, LC, LD, TR>::THREADS, RRP<LA, LB, LC, LD, TR>::MINB)
 eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
-  using K = RRP<LA, LB, LC, LD>;
+  using K = RRP<LA, LB, LC, LD, TR>;
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
   constexpr int QSIZE = K::QSIZE, PSTAGE = K::PSTAGE;
   constexpr bool WL = K::WL;
@@ -370,7 +374,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         });
         double O[K::NAB];
         rr_hrr_regs<LA, LB>(colin, ABv, O);
-        if (!p.transpose_out) {
+        if constexpr (!TR) {
           double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
           static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
         } else {
@@ -378,7 +382,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
         }
       }
-      if (p.transpose_out) sync();
+      if constexpr (TR) sync();
     }
     {
       // ---- coalesced copy-out (see eri_rowreg.cuh) ----------------------------------------
@@ -386,7 +390,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       const unsigned left = ntasks - base;
       const int nvalid = left < (unsigned)QPG ? (int)left : QPG;
       double* __restrict__ o = p.out + (size_t)base * BLK;
-      if (!p.transpose_out) {
+      if constexpr (!TR) {
         if constexpr (LB == 0) {
           for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
             const int q2 = idx / BLK, i = idx - q2 * BLK;

@@ -37,13 +37,13 @@ cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
 }
 
 // uncontracted pair blocks, store mode, more than one row per quartet: pipelined kernel
-template <int LA, int LB, int LC, int LD>
-cudaError_t launch_rowreg_prim(const EriParams& p, const RowInfo* rows, int num_sms,
-                               cudaStream_t stream) {
-  using K = RRP<LA, LB, LC, LD>;
+template <int LA, int LB, int LC, int LD, bool TR>
+cudaError_t launch_rowreg_prim_tr(const EriParams& p, const RowInfo* rows, int num_sms,
+                                  cudaStream_t stream) {
+  using K = RRP<LA, LB, LC, LD, TR>;
   constexpr int SMEM = K::QPC * K::QSIZE * 8;
   static_assert(SMEM <= kSmemLimit, "pipelined row-register kernel exceeds shared memory");
-  auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD>;
+  auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD, TR>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -61,6 +61,17 @@ cudaError_t launch_rowreg_prim(const EriParams& p, const RowInfo* rows, int num_
   if (grid < 1) return cudaSuccess;
   kern<<<(unsigned)grid, K::THREADS, SMEM, stream>>>(p, rows);
   return cudaGetLastError();
+}
+template <int LA, int LB, int LC, int LD>
+cudaError_t launch_rowreg_prim(const EriParams& p, const RowInfo* rows, int num_sms,
+                               cudaStream_t stream) {
+  if constexpr (LA == LC && LB == LD) {
+    // a diagonal class is always launched in its natural orientation (launch_class)
+    return launch_rowreg_prim_tr<LA, LB, LC, LD, false>(p, rows, num_sms, stream);
+  } else {
+    return p.transpose_out ? launch_rowreg_prim_tr<LA, LB, LC, LD, true>(p, rows, num_sms, stream)
+                           : launch_rowreg_prim_tr<LA, LB, LC, LD, false>(p, rows, num_sms, stream);
+  }
 }
 
 template <int LA, int LB, int LC, int LD, int MODE>

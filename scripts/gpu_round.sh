@@ -7,7 +7,8 @@ O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
-for c in ${NCU_CLASSES:-"2222 2121 1111 0000"}; do
+CLS=${NCU_CLASSES:-2222 2121 1111 0000}
+for c in $CLS; do
   a=$(echo $c | sed 's/./& /g')
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:eri_rowreg -s 1 -c 1 -f -o /tmp/prof_$c \
     python scripts/prof_class.py $a 1048576 2 > $O/prof_$c.log 2>&1
