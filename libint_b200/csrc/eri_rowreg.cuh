@@ -261,7 +261,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const RowInfo ri = rows[rmeta.row];
     rmeta.e = ri.e;
     for (int d = 0; d < 3; ++d) {
-      rmeta.rm[d] = ri.rm[d];
+      rmeta.rm[d] = lane_on ? ri.rm[d] : 0;   // leftover lanes read (and discard) row 0's slots
       rmeta.q[d] = (double)ri.q[d];
     }
   }

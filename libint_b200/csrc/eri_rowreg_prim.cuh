@@ -56,7 +56,7 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int P2_DOUBLES = OFF_B2 + (LB > 0 ? B::NCD * B::RTP : 0);
   static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
-#define LB200_PRIM_MINB_HI 3
+#define LB200_PRIM_MINB_HI 4
 #endif
 #ifndef LB200_PRIM_MINB_MID
 #define LB200_PRIM_MINB_MID 5
@@ -95,7 +95,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const RowInfo ri = rows[rmeta.row];
     rmeta.e = ri.e;
     for (int d = 0; d < 3; ++d) {
-      rmeta.rm[d] = ri.rm[d];
+      rmeta.rm[d] = lane_on ? ri.rm[d] : 0;   // leftover lanes read (and discard) row 0's slots
       rmeta.q[d] = (double)ri.q[d];
     }
   }

@@ -13,7 +13,7 @@ constexpr int kBoysTableMmax = 24;    // table rows per interval - 1
 // One primitive pair of a shell pair: what ShellPair::PrimPairData holds in the reference
 // (include/libint2/shell.h:1084-1092) plus what Engine::compute2 derives from it per quartet
 // (PA, gamma, c_a*c_b; engine.impl.h:1331-1367,1514-1537), computed once instead.
-struct PrimPair {
+struct alignas(16) PrimPair {   // 16-byte aligned: records move as 128-bit loads / cp.async pieces
   double P[3];    // (alpha_a A + alpha_b B)/gamma  (shell.h:1186-1194)
   double PA[3];   // P - A; exactly 0 when b is the unit shell (3-centre bra, engine.impl.h:1515)
   double Kc;      // sqrt(2) pi^(5/4) exp(-rho |AB|^2)/gamma * c_a * c_b   (shell.h:1241-1243)
