@@ -59,5 +59,3 @@ def test_three_center_sweep_vs_oracle(oracle):
                           rtol=1e-12, atol=1e-14)
             checked += 1
     assert checked == 3 * len(tc.classes())
-    del tc
-    ctx.close()
