@@ -132,6 +132,9 @@ int lb200_fock_destroy(lb200_fock* f);
 int lb200_fock_schwarz(const lb200_fock* f, double* K /* nshell*nshell, host */);
 /* rank that owns the quartet (bra pair | ket pair), pairs named by their canonical index
  * s1*(s1+1)/2 + s2 (s1 >= s2); host-callable copy of the rule the screening kernel applies.
+ * Ownership goes by the BRA pair alone (bra = the pair of the class with the larger
+ * angular-momentum key, or the larger canonical index inside one class), so every rank
+ * enumerates only its own rows of the task matrix.
  * Replaces the reference's thread round-robin s1234 % nthreads (hartree-fock++.cc:1665). */
 int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks);
 /* G = 1/2 (g + g^T), g accumulated as in hartree-fock++.cc:1721-1743 from density D (nbf x nbf,

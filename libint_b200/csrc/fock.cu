@@ -29,6 +29,7 @@ using namespace lb200;
 
 struct FockClass {
   int la, lb, pa, pb;
+  int bucket = 0;   // contraction-degree bucket of the block's pairs
   lb200_pairs* pairs = nullptr;
   std::vector<double> schwarz;  // sorted descending, same order as pairs
 };
@@ -160,13 +161,18 @@ __global__ void absmax_kernel(const double* __restrict__ x, long long n, double*
   }
 }
 
-// which rank computes the quartet (bra pair gi | ket pair gj): a multiplicative hash of the
-// two canonical pair indices, so that every class and every Schwarz-magnitude range is spread
-// evenly over the ranks (the reference's static round-robin s1234 % nthreads,
-// hartree-fock++.cc:1665, needs a serial counter)
-__host__ __device__ inline int task_owner(int gi, int gj, int nranks) {
-  const unsigned h = (unsigned)gi * 2654435761u + (unsigned)gj * 40503u;
-  return (int)((h >> 8) % (unsigned)nranks);
+// which rank computes the quartet (bra pair gi | ket pair gj): a mixing hash of the canonical
+// index of the BRA pair (the row of the task matrix: the pair of the class with the larger order
+// key, or the larger canonical index inside one class).  Whole rows are owned by one rank, so a
+// rank enumerates and screens only its own rows (the host zeroes the candidate count of the
+// others) -- with ~10^5 rows per build the shares are even to about a percent.  Replaces the
+// reference's serial round-robin s1234 % nthreads (hartree-fock++.cc:1665).
+__host__ __device__ inline int task_owner(int gi, int /*gj*/, int nranks) {
+  unsigned h = (unsigned)gi * 2654435761u;
+  h ^= h >> 15;
+  h *= 2246822519u;
+  h ^= h >> 13;
+  return (int)(h % (unsigned)nranks);
 }
 
 struct ScreenParams {
@@ -331,6 +337,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ksh[x] > ksh[y]; });
     FockClass fc;
     fc.la = kv.first[0]; fc.lb = kv.first[1]; fc.pa = kv.first[2]; fc.pb = kv.first[3];
+    fc.bucket = kv.first[4];
     std::vector<int> as(n), bs_(n);
     fc.schwarz.resize(n);
     for (int i = 0; i < n; ++i) {
@@ -428,7 +435,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   std::vector<unsigned> jmax;
   // LB200_FOCK_PROFILE=1: per class-pair device time (one sync per launch; diagnostics only)
   const bool profile = stats && std::getenv("LB200_FOCK_PROFILE");
-  struct Prof { int c[4]; double ms, nq; };
+  struct Prof { int c[6]; double ms, nq; };
   std::vector<Prof> prof;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
@@ -454,6 +461,13 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
             if (Kt.schwarz[mid] >= thr) lo = mid + 1; else hi = mid;
           }
           jmax[i] = (unsigned)lo;
+        }
+      }
+      if (nranks > 1) {   // rows of other ranks: nothing to enumerate
+        const std::vector<int>& sh = B.pairs->shell;
+        for (int i = 0; i < nb; ++i) {
+          const long long hi = std::max(sh[2 * i], sh[2 * i + 1]), lo = std::min(sh[2 * i], sh[2 * i + 1]);
+          if (task_owner((int)(hi * (hi + 1) / 2 + lo), 0, nranks) != rank) jmax[i] = 0;
         }
       }
       if ((long long)nb > f->jmax_cap) {
@@ -507,10 +521,11 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
             cudaMemcpy(&c, f->d_count, 4, cudaMemcpyDeviceToHost);
             bool found = false;
             for (auto& e : prof)
-              if (e.c[0] == B.la && e.c[1] == B.lb && e.c[2] == Kt.la && e.c[3] == Kt.lb) {
+              if (e.c[0] == B.la && e.c[1] == B.lb && e.c[2] == Kt.la && e.c[3] == Kt.lb &&
+                  e.c[4] == B.bucket && e.c[5] == Kt.bucket) {
                 e.ms += ms; e.nq += c; found = true;
               }
-            if (!found) prof.push_back(Prof{{B.la, B.lb, Kt.la, Kt.lb}, ms, (double)c});
+            if (!found) prof.push_back(Prof{{B.la, B.lb, Kt.la, Kt.lb, B.bucket, Kt.bucket}, ms, (double)c});
           }
           if (stats) {  // optional accounting costs a sync per chunk
             unsigned c = 0;
@@ -529,8 +544,9 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
     for (auto& e : prof) tot += e.ms;
     std::fprintf(stderr, "lb200 fock profile: %zu class pairs, %.2f ms in class kernels\n", prof.size(), tot);
     for (auto& e : prof)
-      std::fprintf(stderr, "  (%d%d|%d%d) %10.3f ms %5.1f%% %12.0f quartets %8.2f ns/quartet\n", e.c[0], e.c[1],
-                   e.c[2], e.c[3], e.ms, 100 * e.ms / tot, e.nq, e.nq > 0 ? 1e6 * e.ms / e.nq : 0.0);
+      std::fprintf(stderr, "  (%d%d|%d%d) buckets %d,%d %10.3f ms %5.1f%% %12.0f quartets %8.2f ns/quartet\n",
+                   e.c[0], e.c[1], e.c[2], e.c[3], e.c[4], e.c[5], e.ms, 100 * e.ms / tot, e.nq,
+                   e.nq > 0 ? 1e6 * e.ms / e.nq : 0.0);
     cudaEventDestroy(pe0);
     cudaEventDestroy(pe1);
   }

@@ -17,3 +17,11 @@ C = rng.standard_normal((n, max(1, n // 8))) / np.sqrt(n)
 D = C @ C.T
 G = f.build(D, 1e-10)
 t0 = time.time(); G, st = f.build(D, 1e-10, stats=True); print("build %.3f s" % (time.time() - t0), st)
+if len(sys.argv) > 3:   # one rank's share of an N-rank build (strong-scaling estimate on one GPU)
+    os.environ.pop("LB200_FOCK_PROFILE", None)
+    for N in [int(x) for x in sys.argv[3].split(",")]:
+        ts = []
+        for r in range(min(N, 2)):
+            f.build(D, 1e-10, rank=r, nranks=N)
+            t0 = time.time(); f.build(D, 1e-10, rank=r, nranks=N); ts.append(time.time() - t0)
+        print("nranks %d: rank shares %s s" % (N, ", ".join("%.3f" % t for t in ts)))
