@@ -40,7 +40,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // TR: the caller's bra is this kernel's unrolled side, results leave as [cd][ab] through the
 // transposing copy-out.  TR = false with LB > 0 stores straight from the bra-HRR lanes and needs
 // no staging buffer for the final integrals: a third less shared memory, one more CTA per SM.
-template <int LA, int LB, int LC, int LD, bool TR>
+// FOCK: the finished shell set is digested into the Fock matrix (fock_digest.cuh) instead of
+// stored; tasks come from the screening kernel's device-side list, the per-quartet engine
+// precision and degeneracy (hartree-fock++.cc:1667-1703) are prefetched with the task.
+template <int LA, int LB, int LC, int LD, bool TR, bool FOCK = false>
 struct RRP : RRK<LA, LB, LC, LD> {
   using B = RRK<LA, LB, LC, LD>;
   // pipeline stage (doubles): bra record 12 | ket record 12 | A-B 3 | C-D 3 | prep 4 | F_m
@@ -51,9 +54,10 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int OFF_X = PIPE;
   static constexpr int VRR_DOUBLES = OFF_X + (B::EMAX > 0 ? B::XSLOTS * B::NECX : 0);
   static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
-  static constexpr bool HAS_FIN = TR || LB == 0;
+  static constexpr bool HAS_FIN = TR || LB == 0 || FOCK;
   static constexpr int OFF_B2 = OFF_FIN + (HAS_FIN ? B::NAB * B::CS : 0);  // row -> column transpose buffer
-  static constexpr int P2_DOUBLES = OFF_B2 + (LB > 0 ? B::NCD * B::RTP : 0);
+  static constexpr int P2_DOUBLES =
+      OFF_B2 + cmax(FOCK ? B::NAB * B::NCD : 0, LB > 0 ? B::NCD * B::RTP : 0);
   static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
 #define LB200_PRIM_MINB_HI 4
@@ -68,10 +72,11 @@ struct RRP : RRK<LA, LB, LC, LD> {
       B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);
 };
 
-template <int LA, int LB, int LC, int LD, bool TR>
-__global__ void __launch_bounds__(RRP<LA, LB, LC, LD, TR>::THREADS, RRP<LA, LB, LC, LD, TR>::MINB)
+template <int LA, int LB, int LC, int LD, bool TR, bool FOCK>
+__global__ void __launch_bounds__(RRP<LA, LB, LC, LD, TR, FOCK>::THREADS, RRP<LA, LB, LC, LD, TR, FOCK>::MINB)
 eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
-  using K = RRP<LA, LB, LC, LD, TR>;
+  using K = RRP<LA, LB, LC, LD, TR, FOCK>;
+  static_assert(!(FOCK && TR), "Fock mode has no output orientation");
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
   constexpr int QSIZE = K::QSIZE, PSTAGE = K::PSTAGE;
   constexpr bool WL = K::WL;
@@ -163,16 +168,52 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       }
     }
   };
+  // Fock mode: shells of a task, then max |D| over the six blocks and the degeneracy
+  // (hartree-fock++.cc:1667-1703); loaded one pipeline step ahead of their use
+  struct Shl { int s1, s2, s3, s4; };
+  auto load_shells = [&](int2 tk) -> Shl {
+    Shl h{0, 0, 0, 0};
+    if constexpr (FOCK) {
+      if (tk.x >= 0) {
+        h.s1 = p.bra.shell[2 * tk.x]; h.s2 = p.bra.shell[2 * tk.x + 1];
+        h.s3 = p.ket.shell[2 * tk.y]; h.s4 = p.ket.shell[2 * tk.y + 1];
+      }
+    }
+    return h;
+  };
+  struct Scr { double dn, deg; };
+  auto load_screen = [&](const Off& o, const Shl& h) -> Scr {
+    Scr c{0.0, 1.0};
+    if constexpr (FOCK) {
+      if (o.ib >= 0) {
+        const double* Dn = p.Dnorm;
+        const int ns = p.nshell;
+        double dn = fmax(Dn[h.s1 * ns + h.s2], Dn[h.s1 * ns + h.s3]);
+        dn = fmax(dn, Dn[h.s2 * ns + h.s3]);
+        dn = fmax(dn, Dn[h.s1 * ns + h.s4]);
+        dn = fmax(dn, Dn[h.s2 * ns + h.s4]);
+        dn = fmax(dn, Dn[h.s3 * ns + h.s4]);
+        c.dn = dn;
+        const double d12 = (h.s1 == h.s2) ? 1.0 : 2.0, d34 = (h.s3 == h.s4) ? 1.0 : 2.0;
+        const bool same = (h.s1 == h.s3 && h.s2 == h.s4) || (h.s1 == h.s4 && h.s2 == h.s3);
+        c.deg = d12 * d34 * (same ? 1.0 : 2.0);
+      }
+    }
+    return c;
+  };
   // Boys lanes, first half: T, pfac (registers), 1/(zeta+eta), rho, on (published by row 0)
   struct BoysState { double T, pfac; bool on; };
-  auto boys_prepare = [&](const Off& o, double* S) -> BoysState {
+  auto boys_prepare = [&](const Off& o, double* S, const Scr& scr) -> BoysState {
     BoysState b{0.0, 0.0, false};
     if (!boys_lane) return b;
     bool on = o.pb >= 0;
     double oogpq = 0.0, rho = 0.0;
     if (on) {
       const double lnb = S[K::S_BP + 9], lnk = S[K::S_KP + 9];
-      on = lnb + lnk > p.ln_precision;   // engine.impl.h:1313-1314
+      double ln_prec = p.ln_precision;
+      if constexpr (FOCK)   // hartree-fock++.cc:1667-1695
+        ln_prec = scr.dn != 0.0 ? log(p.fock_precision / scr.dn) : p.ln_needed_engine_precision;
+      on = lnb + lnk > ln_prec;   // engine.impl.h:1313-1314
     }
     if (on) {
       const double PQx = S[K::S_BP + 0] - S[K::S_KP + 0], PQy = S[K::S_BP + 1] - S[K::S_KP + 1],
@@ -215,16 +256,21 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
   // ---- prologue: round 0 of this group, unpipelined ---------------------------------------
   int2 tk_next;
+  Off ocur;
+  double deg_cur = 1.0;
   {
     const int2 tk0 = load_task(base);
     tk_next = load_task(base + stride);
-    const Off o0 = load_off(tk0);
-    issue_records(o0, Q);
+    ocur = load_off(tk0);
+    const Scr c0 = load_screen(ocur, load_shells(tk0));
+    deg_cur = c0.deg;
+    issue_records(ocur, Q);
     cp_async_wait_all();
     sync();
-    const BoysState b0 = boys_prepare(o0, Q);
+    const BoysState b0 = boys_prepare(ocur, Q, c0);
     boys_finish(b0, Q);
   }
+  Shl shl_next = load_shells(tk_next);
 
   for (int round = 0; base < ntasks; base += stride, ++round) {
     double* const S = Q + (round & 1) * PSTAGE;          // this round's stage
@@ -299,6 +345,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     // next round's records: the stage SN was last read before this round's top barrier
     issue_records(onext, SN);
+    const Scr scr_next = load_screen(onext, shl_next);   // Fock: consumed by boys_prepare below
 
     // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -----------------------
     double* Xq = Q + K::OFF_X;
@@ -357,7 +404,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     sync();                // ... and everybody else's; transposed rows visible
 
     // ---- next round, Boys lanes: T, pfac, 1/(zeta+eta), rho; touch the table row ----------
-    const BoysState bn = boys_prepare(onext, SN);
+    const BoysState bn = boys_prepare(onext, SN, scr_next);
     const double touched = boys_touch(bn);
 
     if constexpr (LB > 0) {
@@ -374,7 +421,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         });
         double O[K::NAB];
         rr_hrr_regs<LA, LB>(colin, ABv, O);
-        if constexpr (!TR) {
+        if constexpr (!TR && !FOCK) {
           double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
           static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
         } else {
@@ -382,9 +429,13 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
         }
       }
-      if constexpr (TR) sync();
+      if constexpr (TR || FOCK) sync();
     }
-    {
+    if constexpr (FOCK) {
+      // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet ------------
+      fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && on, rmeta.row, Q + K::OFF_FIN, K::CS,
+                                           Q + K::OFF_B2, ocur.ib, ocur.ik, deg_cur);
+    } else {
       // ---- coalesced copy-out (see eri_rowreg.cuh) ----------------------------------------
       constexpr int BLK = K::NAB * K::NCD;
       const unsigned left = ntasks - base;
@@ -415,6 +466,9 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       boys_finish(b2, SN);
     }
     tk_next = tk_next2;
+    ocur = onext;
+    deg_cur = scr_next.deg;
+    shl_next = load_shells(tk_next);
   }
 }
 

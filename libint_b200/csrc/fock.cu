@@ -502,6 +502,9 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
           p.tasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
           p.work_counter = f->d_count + 1;
+          // uncontracted x uncontracted bucket: the pipelined kernel (LB200_NO_PRIM_KERNEL=1: A/B)
+          static const bool no_prim = std::getenv("LB200_NO_PRIM_KERNEL") != nullptr;
+          p.uncontracted = (!no_prim && p.bra.max_nprim <= 1 && p.ket.max_nprim <= 1) ? 1 : 0;
           p.boys = ctx->d_boys;
           p.screening = kScreenSchwarzInf;
           p.D = f->d_D; p.F = f->d_F; p.nbf = n; p.Dnorm = f->d_Dnorm; p.nshell = ns;

@@ -37,13 +37,13 @@ cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
 }
 
 // uncontracted pair blocks, store mode, more than one row per quartet: pipelined kernel
-template <int LA, int LB, int LC, int LD, bool TR>
+template <int LA, int LB, int LC, int LD, bool TR, bool FOCK = false>
 cudaError_t launch_rowreg_prim_tr(const EriParams& p, const RowInfo* rows, int num_sms,
                                   cudaStream_t stream) {
-  using K = RRP<LA, LB, LC, LD, TR>;
+  using K = RRP<LA, LB, LC, LD, TR, FOCK>;
   constexpr int SMEM = K::QPC * K::QSIZE * 8;
   static_assert(SMEM <= kSmemLimit, "pipelined row-register kernel exceeds shared memory");
-  auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD, TR>;
+  auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD, TR, FOCK>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -95,8 +95,18 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
     q.ket = p.bra;
     q.swap_tasks = p.swap_tasks ^ 1;
     q.transpose_out = p.transpose_out ^ 1;
-    if constexpr (MODE != kModeFock && RR<LC, LD, LA, LB>::NEC > 1) {
-      if (p.uncontracted) return launch_rowreg_prim<LC, LD, LA, LB>(q, rows, num_sms, stream);
+    if constexpr (RR<LC, LD, LA, LB>::NEC > 1) {
+      if (p.uncontracted) {
+        // Fock mode: measured on (H2O)_64/def2-TZVP the pipelined kernel wins only for the
+        // (ps| row classes (5-15 %); with more rows per quartet the digestion's shared-memory and
+        // register footprint costs more than the hidden latency gains, so those stay general
+        if constexpr (MODE == kModeFock) {
+          if constexpr (RR<LC, LD, LA, LB>::NEC <= 4)
+            return launch_rowreg_prim_tr<LC, LD, LA, LB, false, true>(q, rows, num_sms, stream);
+        } else {
+          return launch_rowreg_prim<LC, LD, LA, LB>(q, rows, num_sms, stream);
+        }
+      }
     }
     return launch_rowreg<LC, LD, LA, LB, MODE>(q, rows, num_sms, stream);
   } else {
