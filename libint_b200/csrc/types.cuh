@@ -74,7 +74,6 @@ struct EriParams {
   double fock_precision;
   double ln_needed_engine_precision;
   double needed_engine_precision;
-  double deg_scale;          // unused by store modes
 };
 
 }  // namespace lb200
