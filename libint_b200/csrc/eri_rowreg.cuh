@@ -96,7 +96,16 @@ struct RR {
   static constexpr int NG = THREADS / GROUP;
   // CTAs per SM the register allocation is bounded for (measured per pyramid depth: the F = 4
   // pyramid wants the full 255 registers, shallower ones gain more from a third / fourth CTA)
-  static constexpr int MINB = FMAX >= 4 ? 2 : (FMAX >= 2 ? 3 : 4);
+  // Thread-per-quartet classes (NEC = 1) are latency-bound in the Fock build (long scoreboard
+  // ~23 cycles per issue for uncontracted (ps|ss)): more resident warps pay there.
+#ifndef LB200_TQ_MINB_LO
+#define LB200_TQ_MINB_LO 4
+#endif
+#ifndef LB200_TQ_MINB_MID
+#define LB200_TQ_MINB_MID 3
+#endif
+  static constexpr int MINB = NEC == 1 ? (FMAX >= 4 ? 2 : (FMAX >= 2 ? LB200_TQ_MINB_MID : LB200_TQ_MINB_LO))
+                                       : (FMAX >= 4 ? 2 : (FMAX >= 2 ? 3 : 4));
   static constexpr int QPC = NG * QPG;                // quartets in flight per CTA
 };
 
