@@ -46,6 +46,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <int LA, int LB, int LC, int LD, bool TR, bool FOCK = false>
 struct RRP : RRK<LA, LB, LC, LD> {
   using B = RRK<LA, LB, LC, LD>;
+  // CTA shape of this kernel: 35 rows per quartet ((dd| / (fp| rows) waste 18 % of a 128-lane CTA
+  // (3 quartets); 256 lanes would hold 7 (96 %).  Measured: no gain ((dd|dd) 36.6 vs 36.5 ms per
+  // 10^7 quartets) -- the kernel is bound by the latency of its FP64 dependency chains at 4 warps
+  // per scheduler, not by lane utilisation -- so the narrow CTA stays the default.
+#ifndef LB200_PRIM_WIDE35
+#define LB200_PRIM_WIDE35 0
+#endif
+  static constexpr int THREADS = (B::NEC == 35 && LB200_PRIM_WIDE35) ? 256 : B::THREADS;
+  static constexpr int GROUP = B::WL ? 32 : THREADS;
+  static constexpr int QPG = GROUP / B::NEC;
+  static constexpr int NG = THREADS / GROUP;
+  static constexpr int QPC = NG * QPG;
   // pipeline stage (doubles): bra record 12 | ket record 12 | A-B 3 | C-D 3 | prep 4 | F_m
   static constexpr int S_BP = 0, S_KP = 12, S_AB = 24, S_CD = 27, S_PREP = 30, S_F = 34;
   static constexpr int PSTAGE = (S_F + B::L + 1 + 1) & ~1;
@@ -68,8 +80,9 @@ struct RRP : RRK<LA, LB, LC, LD> {
 #ifndef LB200_PRIM_MINB_LO
 #define LB200_PRIM_MINB_LO 6
 #endif
-  static constexpr int MINB =
+  static constexpr int MINB128 =
       B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);
+  static constexpr int MINB = THREADS == 256 ? cmax(1, MINB128 / 2) : MINB128;
 };
 
 template <int LA, int LB, int LC, int LD, bool TR, bool FOCK>
