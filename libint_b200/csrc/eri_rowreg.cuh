@@ -292,7 +292,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       ccnt_[k] = (double)c;
     });
   }
-  double* const Q = smem + (size_t)(lane_on ? q : 0) * QSIZE;  // this lane's quartet region
+  double* const Q = smem + (size_t)(lane_on ? q : g * QPG) * QSIZE;  // this lane's quartet region
 
   const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
   if constexpr (!WL) {

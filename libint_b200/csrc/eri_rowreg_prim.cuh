@@ -134,7 +134,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       ccnt_[k] = (double)c;
     });
   }
-  double* const Q = smem + (size_t)(lane_on ? q : 0) * QSIZE;
+  double* const Q = smem + (size_t)(lane_on ? q : g * QPG) * QSIZE;
   const bool boys_lane = lane_on && rmeta.row <= L;
 
   const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
