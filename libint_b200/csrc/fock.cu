@@ -30,6 +30,7 @@ using namespace lb200;
 struct FockClass {
   int la, lb, pa, pb;
   int bucket = 0;   // contraction-degree bucket of the block's pairs
+  double* d_dn = nullptr;   // device, [npair]: Dnorm(shell1, shell2) of every pair, refreshed per build
   lb200_pairs* pairs = nullptr;
   std::vector<double> schwarz;  // sorted descending, same order as pairs
 };
@@ -180,6 +181,9 @@ struct ScreenParams {
   int same_class;
   int row0, nrow;            // bra rows of this chunk
   const unsigned* jmax;      // per bra row (relative to row0): number of ket candidates
+  const double* bra_dn;      // [npair] Dnorm of the pair's own block (D12 / D34)
+  const double* ket_dn;
+  int stage_rows;            // 1: the two Dnorm rows of the bra shells fit in shared memory
   const double* Dnorm;
   int nshell;
   double fock_precision;
@@ -190,34 +194,58 @@ struct ScreenParams {
   unsigned cap;
 };
 
-// unique-quartet rule and Schwarz x density screen, hartree-fock++.cc:1628-1677
+// per-pair Dnorm(shell1, shell2): the D12 / D34 operand of the screen, one coalesced array per
+// block instead of a random gather per candidate
+__global__ void pair_dnorm_kernel(const int* __restrict__ shell, int npair, const double* __restrict__ Dn,
+                                  int ns, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += gridDim.x * blockDim.x)
+    out[i] = Dn[(size_t)shell[2 * i] * ns + shell[2 * i + 1]];
+}
+
+// unique-quartet rule and Schwarz x density screen, hartree-fock++.cc:1628-1677.
+// One CTA per bra row: the rows Dnorm(s1, :) and Dnorm(s2, :) -- four of the six |D| operands of
+// every candidate of that row -- are staged in shared memory when the row has enough candidates
+// to pay for it; D12 and D34 come from the per-pair arrays.  What is left per candidate is 28
+// coalesced bytes of ket-pair data and four shared-memory gathers.
 __global__ void screen_kernel(const ScreenParams p) {
+  extern __shared__ double s_rows[];   // [2][nshell] when p.stage_rows
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int wid = threadIdx.x >> 5;
-  for (int r = blockIdx.x * warps_per_block + wid; r < p.nrow; r += gridDim.x * warps_per_block) {
+  const int ns = p.nshell;
+  for (int r = blockIdx.x; r < p.nrow; r += gridDim.x) {
     const int i = p.row0 + r;
     const unsigned jm = p.jmax[r];
+    if (jm == 0) continue;
     const int s1 = p.bra.shell[2 * i], s2 = p.bra.shell[2 * i + 1];
     const double Ki = p.bra.schwarz[i];
     const int gi = p.bra.gidx[i];
-    const double* Dn = p.Dnorm;
-    const int ns = p.nshell;
-    const double D12 = Dn[s1 * ns + s2];
-    for (unsigned j0 = 0; j0 < jm; j0 += 32) {
-      const unsigned j = j0 + lane;
+    const double D12 = p.bra_dn[i];
+    const double* r1 = p.Dnorm + (size_t)s1 * ns;
+    const double* r2 = p.Dnorm + (size_t)s2 * ns;
+    const bool staged = p.stage_rows && jm >= 4u * blockDim.x;
+    if (staged) {
+      __syncthreads();   // previous row's readers are done
+      for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+        s_rows[k] = r1[k];
+        s_rows[ns + k] = r2[k];
+      }
+      __syncthreads();
+      r1 = s_rows;
+      r2 = s_rows + ns;
+    }
+    for (unsigned j0 = 0; j0 < jm; j0 += blockDim.x) {
+      const unsigned j = j0 + threadIdx.x;
       bool keep = false;
       if (j < jm) {
         const int gj = p.ket.gidx[j];
         keep = !p.same_class || gi >= gj;
         if (keep && p.nranks > 1) keep = task_owner(gi, gj, p.nranks) == p.rank;
         if (keep && p.use_schwarz) {
-          const int s3 = p.ket.shell[2 * j], s4 = p.ket.shell[2 * j + 1];
-          double dn = fmax(D12, Dn[s1 * ns + s3]);
-          dn = fmax(dn, Dn[s2 * ns + s3]);
-          dn = fmax(dn, Dn[s1 * ns + s4]);
-          dn = fmax(dn, Dn[s2 * ns + s4]);
-          dn = fmax(dn, Dn[s3 * ns + s4]);
+          const int2 s34 = reinterpret_cast<const int2*>(p.ket.shell)[j];
+          double dn = fmax(D12, r1[s34.x]);
+          dn = fmax(dn, r2[s34.x]);
+          dn = fmax(dn, r1[s34.y]);
+          dn = fmax(dn, r2[s34.y]);
+          dn = fmax(dn, p.ket_dn[j]);
           const double Kj = p.ket.schwarz[j];
           // reference multiplies Dnorm * K(s1,s2) * K(s3,s4) with (s1,s2) the larger pair
           const double est = gi >= gj ? dn * Ki * Kj : dn * Kj * Ki;
@@ -348,6 +376,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
     rc = build_pairs(ctx, obs, obs, n, as.data(), bs_.data(), kScreenSchwarzInf,
                      ln_max_engine_precision, nullptr, fc.schwarz.data(), &fc.pairs);
     if (rc) break;
+    if (cudaMalloc(&fc.d_dn, std::max(1, n) * sizeof(double)) != cudaSuccess) { rc = LB200_ERR_NOMEM; break; }
     f->classes.push_back(std::move(fc));
   }
   if (rc) { lb200_fock_destroy(f); return rc; }
@@ -373,7 +402,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
 int lb200_fock_destroy(lb200_fock* f) {
   if (!f) return LB200_OK;
   cudaSetDevice(f->ctx->device);
-  for (auto& c : f->classes) lb200_pairs_destroy(c.pairs);
+  for (auto& c : f->classes) { lb200_pairs_destroy(c.pairs); cudaFree(c.d_dn); }
   cudaFree(f->d_D); cudaFree(f->d_F); cudaFree(f->d_Dnorm); cudaFree(f->d_scalar);
   cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize); cudaFree(f->d_tasks); cudaFree(f->d_count);
   cudaFree(f->d_jmax);
@@ -418,6 +447,13 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   absmax_kernel<<<std::min(1024, (ns * ns + 255) / 256), 256, 0, st>>>(f->d_Dnorm, (long long)ns * ns,
                                                                      f->d_scalar);
   ctx->launches += 2;
+  for (auto& c : f->classes) {
+    const int np = c.pairs->dev.npair;
+    if (np == 0) continue;
+    pair_dnorm_kernel<<<std::min(1024, (np + 255) / 256), 256, 0, st>>>(c.pairs->dev.shell, np, f->d_Dnorm,
+                                                                      ns, c.d_dn);
+    ++ctx->launches;
+  }
   double Dmax = 0;
   cudaMemcpyAsync(&Dmax, f->d_scalar, 8, cudaMemcpyDeviceToHost, st);
   if ((rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock: D norms"))) return rc;
@@ -490,13 +526,22 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           sp.row0 = row; sp.nrow = r1 - row;
           sp.jmax = f->d_jmax + row;
           sp.Dnorm = f->d_Dnorm; sp.nshell = ns;
+          sp.bra_dn = B.d_dn; sp.ket_dn = Kt.d_dn;
           sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
           sp.rank = rank; sp.nranks = nranks;
           sp.tasks = f->d_tasks; sp.count = f->d_count; sp.cap = (unsigned)cap;
           cudaMemsetAsync(f->d_count, 0, 8, st);
-          const int wpb = 8;
-          const int grid = std::min(ctx->num_sms * 8, (sp.nrow + wpb - 1) / wpb);
-          screen_kernel<<<grid, wpb * 32, 0, st>>>(sp);
+          const int threads = 128;
+          const size_t row_bytes = 2 * (size_t)ns * sizeof(double);
+          sp.stage_rows = row_bytes <= (size_t)96 * 1024;
+          const size_t smem = sp.stage_rows ? row_bytes : 0;
+          static bool attr_set = false;
+          if (!attr_set) {
+            cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            attr_set = true;
+          }
+          const int grid = std::min(ctx->num_sms * 16, sp.nrow);
+          screen_kernel<<<grid, threads, smem, st>>>(sp);
           ++ctx->launches;
           EriParams p{};
           p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
@@ -512,6 +557,9 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.needed_engine_precision = needed_engine_precision;
           p.ln_needed_engine_precision = std::log(needed_engine_precision);
           if (profile) cudaEventRecord(pe0, st);
+          // LB200_FOCK_SCREEN_ONLY=1 (diagnostics): enumerate and screen, skip the class kernels
+          static const bool screen_only = std::getenv("LB200_FOCK_SCREEN_ONLY") != nullptr;
+          if (!screen_only)
           rc = check_cuda(ctx, launch_eri(B.la, B.lb, Kt.la, Kt.lb, p, ctx->d_rows, kModeFock,
                                           ctx->num_sms, st), "launch fock kernel");
           ++ctx->launches;
