@@ -403,16 +403,21 @@ def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world):
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     nints = sum(nn * blk for _, nn, blk, _, _ in ev)
-    top = sorted(ev, key=lambda x: -x[3].elapsed_time(x[4]))[:6]
+    agg = {}
+    for c, nn, blk, a, b in ev:   # merge the contraction buckets of a class
+        e = agg.setdefault(c, [0, 0.0])
+        e[0] += nn
+        e[1] += a.elapsed_time(b)
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]
     return {"workload": "C%dH%d (P|mu nu), obs def2-tzvp (%d shells, %d bf), dfbs def2-tzvp-jk (%d shells, %d bf, "
                         "max l %d), %d significant orbital pairs" % (args.df3c_carbons, 2 * args.df3c_carbons + 2,
                                                                       len(obs), obs.nbf, len(dfbs), dfbs.nbf,
                                                                       dfbs.max_l, tc.npairs),
-            "shell_triplets": n, "classes": len(tc.classes()), "seconds": ms * 1e-3,
+            "shell_triplets": n, "classes": len(tc.classes()), "launch_groups": len(tc.blocks()), "seconds": ms * 1e-3,
             "triplets_per_s": n / (ms * 1e-3), "cartesian_integrals": nints,
             "hbm_write_gbs": nints * 8 / (ms * 1e-3) / 1e9, "setup_seconds": setup_s,
             "slowest_classes": [{"class": "(%d s|%d %d)" % c, "triplets": nn,
-                                 "ns_per_triplet": 1e6 * a.elapsed_time(b) / nn} for c, nn, _, a, b in top]}
+                                 "ns_per_triplet": 1e6 * t / nn} for c, (nn, t) in top]}
 
 
 def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_):

@@ -28,32 +28,45 @@ class ThreeCenter:
         a, b = np.array(s1), np.array(s2)
         sw = lo[a] < lo[b]
         a, b = np.where(sw, b, a), np.where(sw, a, b)
+        # blocks are split by contraction as well (uncontracted | contracted), like the Fock
+        # builder's buckets: the quartets of a launch run their primitive loops in lockstep, and
+        # all-uncontracted launches take the pipelined kernel
+        npo = np.array([s.nprim for s in obs])
+        cb = (npo[a] * npo[b] > 1).astype(int)
         self.kets = {}
-        for key in sorted(set(zip(lo[a].tolist(), lo[b].tolist()))):
-            m = (lo[a] == key[0]) & (lo[b] == key[1])
+        for key in sorted(set(zip(lo[a].tolist(), lo[b].tolist(), cb.tolist()))):
+            m = (lo[a] == key[0]) & (lo[b] == key[1]) & (cb == key[2])
             self.kets[key] = capi.Pairs(ctx, self.B, self.B, a[m], b[m])
         ldf = np.array([s.l for s in dfbs])
+        cdf = (np.array([s.nprim for s in dfbs]) > 1).astype(int)
         self.bras = {}
-        for L in sorted(set(ldf.tolist())):
-            idx = np.nonzero(ldf == L)[0].astype(np.int32)
-            self.bras[L] = capi.Pairs(ctx, self.Bdf, self.unit, idx, np.zeros_like(idx))
+        for key in sorted(set(zip(ldf.tolist(), cdf.tolist()))):
+            idx = np.nonzero((ldf == key[0]) & (cdf == key[1]))[0].astype(np.int32)
+            self.bras[key] = capi.Pairs(ctx, self.Bdf, self.unit, idx, np.zeros_like(idx))
         self.npairs = int(len(a))
 
+    def blocks(self):
+        """(bra key, ket key) of every launch group; bra key = (L, contracted), ket key =
+        (lc, ld, contracted)."""
+        return [(kb, kk) for kb in self.bras for kk in self.kets]
+
     def classes(self):
-        return [(L,) + k for L in self.bras for k in self.kets]
+        """distinct angular-momentum classes (L s|lc ld)."""
+        return sorted(set((kb[0], kk[0], kk[1]) for kb, kk in self.blocks()))
 
     def ntriplets(self):
-        return sum(self.bras[c[0]].npair * self.kets[c[1:]].npair for c in self.classes())
+        return sum(self.bras[kb].npair * self.kets[kk].npair for kb, kk in self.blocks())
 
     def sweep(self, out, chunk_bytes=1 << 30, sink=None, events=None):
         """Every (P|mu nu) shell triplet once, class by class, Cartesian, into the device
-        buffer `out` (torch CUDA float64, reused chunk after chunk).  `sink(cls, t0, n, view)`
-        sees each finished chunk.  Returns the number of shell triplets computed."""
+        buffer `out` (torch CUDA float64, reused chunk after chunk).  `sink((bra key, ket key), t0, n,
+        view)` sees each finished chunk.  Returns the number of shell triplets computed."""
         import torch
         dev = out.device
         total = 0
-        for cls in self.classes():
-            bra, ket = self.bras[cls[0]], self.kets[cls[1:]]
+        for kb, kk in self.blocks():
+            cls = (kb[0], kk[0], kk[1])
+            bra, ket = self.bras[kb], self.kets[kk]
             blk = capi.eri_block_size(bra, ket)
             n = bra.npair * ket.npair
             per = max(1, min(n, min(out.numel(), chunk_bytes // 8) // blk))
@@ -66,7 +79,7 @@ class ThreeCenter:
                 tasks = torch.stack((t // ket.npair, t % ket.npair), dim=1).to(torch.int32).contiguous()
                 capi.eri_batch(self.ctx, bra, ket, tasks, out=out[:m * blk])
                 if sink is not None:
-                    sink(cls, t0, m, out[:m * blk].view(m, blk))
+                    sink((kb, kk), t0, m, out[:m * blk].view(m, blk))
             if events is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record(torch.cuda.current_stream(dev))

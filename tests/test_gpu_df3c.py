@@ -42,9 +42,10 @@ def test_three_center_sweep_vs_oracle(oracle):
     ooff = np.concatenate([[0], np.cumsum(on)])
     doff = np.concatenate([[0], np.cumsum(dn)])
     checked = 0
-    for cls in tc.classes():
-        bra, ket = tc.bras[cls[0]], tc.kets[cls[1:]]
-        blocks = np.concatenate(got[cls], axis=0)
+    for kb, kk in tc.blocks():
+        cls = (kb[0], kk[0], kk[1])
+        bra, ket = tc.bras[kb], tc.kets[kk]
+        blocks = np.concatenate(got[(kb, kk)], axis=0)
         assert blocks.shape[0] == bra.npair * ket.npair
         for _ in range(3):
             ip, jk = int(rng.integers(bra.npair)), int(rng.integers(ket.npair))
@@ -58,4 +59,5 @@ def test_three_center_sweep_vs_oracle(oracle):
             assert_parity(blocks[ip * ket.npair + jk], ref, "(%d s|%d %d) P=%d mu=%d nu=%d" % (cls + (P, a, b)),
                           rtol=1e-12, atol=1e-14)
             checked += 1
-    assert checked == 3 * len(tc.classes())
+    assert checked == 3 * len(tc.blocks())
+    assert len(tc.blocks()) > len(tc.classes())   # contraction buckets split the classes
