@@ -323,8 +323,17 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
     int ib = 0, ik = 0, pb0 = 0, nb = 0, pk0 = 0, nk = 0;
+    double ln_prec = p.ln_precision, prec = p.precision, deg = 1.0;
     if (valid) {
-      const int2 tk = p.tasks[task];
+      int2 tk;
+      if constexpr (FOCK) {   // precision and degeneracy come with the task (screen_kernel)
+        const int4 ft = p.ftasks[task];
+        tk = make_int2(ft.x, ft.y & 0x3fffffff);
+        deg = (double)(1 << ((unsigned)ft.y >> 30));
+        ln_prec = __hiloint2double(ft.w, ft.z);
+      } else {
+        tk = p.tasks[task];
+      }
       ib = p.swap_tasks ? tk.y : tk.x;
       ik = p.swap_tasks ? tk.x : tk.y;
       pb0 = p.bra.prim_off[ib];
@@ -339,31 +348,6 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       if (valid && rmeta.row == 0 && nit > 0) atomicMax(&s_maxit[round % 3], nit);
     }
 
-    // ---- per-quartet screening precision ----------------------------------------------
-    double ln_prec = p.ln_precision, prec = p.precision, deg = 1.0;
-    if constexpr (FOCK) {
-      if (valid) {  // hartree-fock++.cc:1667-1695
-        const int s1 = p.bra.shell[2 * ib], s2 = p.bra.shell[2 * ib + 1];
-        const int s3 = p.ket.shell[2 * ik], s4 = p.ket.shell[2 * ik + 1];
-        const double* Dn = p.Dnorm;
-        const int ns = p.nshell;
-        double dn = fmax(Dn[s1 * ns + s2], Dn[s1 * ns + s3]);
-        dn = fmax(dn, Dn[s2 * ns + s3]);
-        dn = fmax(dn, Dn[s1 * ns + s4]);
-        dn = fmax(dn, Dn[s2 * ns + s4]);
-        dn = fmax(dn, Dn[s3 * ns + s4]);
-        if (dn != 0.0) {
-          prec = p.fock_precision / dn;
-          ln_prec = log(prec);
-        } else {
-          prec = p.needed_engine_precision;
-          ln_prec = p.ln_needed_engine_precision;
-        }
-        const double d12 = (s1 == s2) ? 1.0 : 2.0, d34 = (s3 == s4) ? 1.0 : 2.0;
-        const bool same = (s1 == s3 && s2 == s4) || (s1 == s4 && s2 == s3);
-        deg = d12 * d34 * (same ? 1.0 : 2.0);
-      }
-    }
     double CD[3] = {0, 0, 0};
     if (valid) {
       CD[0] = p.ket.AB[3 * ik]; CD[1] = p.ket.AB[3 * ik + 1]; CD[2] = p.ket.AB[3 * ik + 2];

@@ -146,11 +146,24 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   // ---- pipeline helpers ---------------------------------------------------------------
   // primitive offsets of a task: (first bra primitive, first ket primitive), -1 if the task is
   // out of range or either pair kept no primitive
-  auto load_task = [&](unsigned b) -> int2 {
+  // Fock mode: the task record carries ln(engine precision) and the degeneracy of the quartet
+  // (types.cuh, written by the screening kernel)
+  struct Task { int2 t; double lnp, deg; };
+  auto load_task = [&](unsigned b) -> Task {
     const unsigned t = b + qg;
-    if (!lane_on || t >= ntasks) return make_int2(-1, -1);
-    const int2 tk = p.tasks[t];
-    return p.swap_tasks ? make_int2(tk.y, tk.x) : tk;
+    Task r{make_int2(-1, -1), 0.0, 1.0};
+    if (!lane_on || t >= ntasks) return r;
+    int2 tk;
+    if constexpr (FOCK) {
+      const int4 ft = p.ftasks[t];
+      tk = make_int2(ft.x, ft.y & 0x3fffffff);
+      r.deg = (double)(1 << ((unsigned)ft.y >> 30));
+      r.lnp = __hiloint2double(ft.w, ft.z);
+    } else {
+      tk = p.tasks[t];
+    }
+    r.t = p.swap_tasks ? make_int2(tk.y, tk.x) : tk;
+    return r;
   };
   struct Off { int pb, pk, ib, ik; };   // ib < 0: no task; pb < 0: a pair kept no primitive
   auto load_off = [&](int2 tk) -> Off {
@@ -181,51 +194,16 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       }
     }
   };
-  // Fock mode: shells of a task, then max |D| over the six blocks and the degeneracy
-  // (hartree-fock++.cc:1667-1703); loaded one pipeline step ahead of their use
-  struct Shl { int s1, s2, s3, s4; };
-  auto load_shells = [&](int2 tk) -> Shl {
-    Shl h{0, 0, 0, 0};
-    if constexpr (FOCK) {
-      if (tk.x >= 0) {
-        h.s1 = p.bra.shell[2 * tk.x]; h.s2 = p.bra.shell[2 * tk.x + 1];
-        h.s3 = p.ket.shell[2 * tk.y]; h.s4 = p.ket.shell[2 * tk.y + 1];
-      }
-    }
-    return h;
-  };
-  struct Scr { double dn, deg; };
-  auto load_screen = [&](const Off& o, const Shl& h) -> Scr {
-    Scr c{0.0, 1.0};
-    if constexpr (FOCK) {
-      if (o.ib >= 0) {
-        const double* Dn = p.Dnorm;
-        const int ns = p.nshell;
-        double dn = fmax(Dn[h.s1 * ns + h.s2], Dn[h.s1 * ns + h.s3]);
-        dn = fmax(dn, Dn[h.s2 * ns + h.s3]);
-        dn = fmax(dn, Dn[h.s1 * ns + h.s4]);
-        dn = fmax(dn, Dn[h.s2 * ns + h.s4]);
-        dn = fmax(dn, Dn[h.s3 * ns + h.s4]);
-        c.dn = dn;
-        const double d12 = (h.s1 == h.s2) ? 1.0 : 2.0, d34 = (h.s3 == h.s4) ? 1.0 : 2.0;
-        const bool same = (h.s1 == h.s3 && h.s2 == h.s4) || (h.s1 == h.s4 && h.s2 == h.s3);
-        c.deg = d12 * d34 * (same ? 1.0 : 2.0);
-      }
-    }
-    return c;
-  };
   // Boys lanes, first half: T, pfac (registers), 1/(zeta+eta), rho, on (published by row 0)
   struct BoysState { double T, pfac; bool on; };
-  auto boys_prepare = [&](const Off& o, double* S, const Scr& scr) -> BoysState {
+  auto boys_prepare = [&](const Off& o, double* S, double lnp) -> BoysState {
     BoysState b{0.0, 0.0, false};
     if (!boys_lane) return b;
     bool on = o.pb >= 0;
     double oogpq = 0.0, rho = 0.0;
     if (on) {
       const double lnb = S[K::S_BP + 9], lnk = S[K::S_KP + 9];
-      double ln_prec = p.ln_precision;
-      if constexpr (FOCK)   // hartree-fock++.cc:1667-1695
-        ln_prec = scr.dn != 0.0 ? log(p.fock_precision / scr.dn) : p.ln_needed_engine_precision;
+      const double ln_prec = FOCK ? lnp : p.ln_precision;   // hartree-fock++.cc:1693-1695
       on = lnb + lnk > ln_prec;   // engine.impl.h:1313-1314
     }
     if (on) {
@@ -268,31 +246,29 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   };
 
   // ---- prologue: round 0 of this group, unpipelined ---------------------------------------
-  int2 tk_next;
+  Task tk_next;
   Off ocur;
   double deg_cur = 1.0;
   {
-    const int2 tk0 = load_task(base);
+    const Task tk0 = load_task(base);
     tk_next = load_task(base + stride);
-    ocur = load_off(tk0);
-    const Scr c0 = load_screen(ocur, load_shells(tk0));
-    deg_cur = c0.deg;
+    ocur = load_off(tk0.t);
+    deg_cur = tk0.deg;
     issue_records(ocur, Q);
     cp_async_wait_all();
     sync();
-    const BoysState b0 = boys_prepare(ocur, Q, c0);
+    const BoysState b0 = boys_prepare(ocur, Q, tk0.lnp);
     boys_finish(b0, Q);
   }
-  Shl shl_next = load_shells(tk_next);
 
   for (int round = 0; base < ntasks; base += stride, ++round) {
     double* const S = Q + (round & 1) * PSTAGE;          // this round's stage
     double* const SN = Q + ((round + 1) & 1) * PSTAGE;   // next round's stage
     const bool more = base + stride < ntasks;            // group-uniform
     // ---- top: next round's offsets, the task after that (consumed later in this round) ----
-    const Off onext = more ? load_off(tk_next) : Off{-1, -1, -1, -1};
-    const int2 tk_next2 = (more && base + 2 * stride < ntasks) ? load_task(base + 2 * stride)
-                                                                : make_int2(-1, -1);
+    const Off onext = more ? load_off(tk_next.t) : Off{-1, -1, -1, -1};
+    const Task tk_next2 = (more && base + 2 * stride < ntasks) ? load_task(base + 2 * stride)
+                                                               : Task{make_int2(-1, -1), 0.0, 1.0};
     sync();   // stage S complete (prologue / previous round); previous phase 2 finished
 
     // ---- prerequisites from the stage (engine.impl.h:1331-1367,1389-1392,1602-1641) --------
@@ -358,7 +334,6 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     // next round's records: the stage SN was last read before this round's top barrier
     issue_records(onext, SN);
-    const Scr scr_next = load_screen(onext, shl_next);   // Fock: consumed by boys_prepare below
 
     // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -----------------------
     double* Xq = Q + K::OFF_X;
@@ -417,7 +392,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     sync();                // ... and everybody else's; transposed rows visible
 
     // ---- next round, Boys lanes: T, pfac, 1/(zeta+eta), rho; touch the table row ----------
-    const BoysState bn = boys_prepare(onext, SN, scr_next);
+    const BoysState bn = boys_prepare(onext, SN, tk_next.lnp);
     const double touched = boys_touch(bn);
 
     if constexpr (LB > 0) {
@@ -478,10 +453,9 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       if (touched != touched) b2.pfac = touched;
       boys_finish(b2, SN);
     }
-    tk_next = tk_next2;
     ocur = onext;
-    deg_cur = scr_next.deg;
-    shl_next = load_shells(tk_next);
+    deg_cur = tk_next.deg;
+    tk_next = tk_next2;
   }
 }
 

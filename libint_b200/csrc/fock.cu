@@ -47,7 +47,7 @@ struct lb200_fock {
   double* d_scalar = nullptr;
   int* d_shell2bf = nullptr;
   int* d_shellsize = nullptr;
-  int2* d_tasks = nullptr;
+  int4* d_tasks = nullptr;   // task records (types.cuh: EriParams::ftasks)
   unsigned* d_count = nullptr;
   unsigned* d_jmax = nullptr;
   long long task_cap = 0, jmax_cap = 0;
@@ -187,9 +187,10 @@ struct ScreenParams {
   const double* Dnorm;
   int nshell;
   double fock_precision;
+  double ln_needed_engine_precision;   // used when max |D| of the quartet is 0 (hf++:1693-1695)
   int use_schwarz;
   int rank, nranks;
-  int2* tasks;
+  int4* tasks;
   unsigned* count;
   unsigned cap;
 };
@@ -235,21 +236,26 @@ __global__ void screen_kernel(const ScreenParams p) {
     for (unsigned j0 = 0; j0 < jm; j0 += blockDim.x) {
       const unsigned j = j0 + threadIdx.x;
       bool keep = false;
+      double dn = 0.0;   // Dnorm1234 = 0 without Schwarz screening (hartree-fock++.cc:1666-1672)
+      int code = 0;      // log2 of the permutational degeneracy (hartree-fock++.cc:1683-1687)
       if (j < jm) {
         const int gj = p.ket.gidx[j];
         keep = !p.same_class || gi >= gj;
         if (keep && p.nranks > 1) keep = task_owner(gi, gj, p.nranks) == p.rank;
-        if (keep && p.use_schwarz) {
+        if (keep) {
           const int2 s34 = reinterpret_cast<const int2*>(p.ket.shell)[j];
-          double dn = fmax(D12, r1[s34.x]);
-          dn = fmax(dn, r2[s34.x]);
-          dn = fmax(dn, r1[s34.y]);
-          dn = fmax(dn, r2[s34.y]);
-          dn = fmax(dn, p.ket_dn[j]);
-          const double Kj = p.ket.schwarz[j];
-          // reference multiplies Dnorm * K(s1,s2) * K(s3,s4) with (s1,s2) the larger pair
-          const double est = gi >= gj ? dn * Ki * Kj : dn * Kj * Ki;
-          keep = !(est < p.fock_precision);
+          code = (s1 != s2) + (s34.x != s34.y) + (gi != gj);
+          if (p.use_schwarz) {
+            dn = fmax(D12, r1[s34.x]);
+            dn = fmax(dn, r2[s34.x]);
+            dn = fmax(dn, r1[s34.y]);
+            dn = fmax(dn, r2[s34.y]);
+            dn = fmax(dn, p.ket_dn[j]);
+            const double Kj = p.ket.schwarz[j];
+            // reference multiplies Dnorm * K(s1,s2) * K(s3,s4) with (s1,s2) the larger pair
+            const double est = gi >= gj ? dn * Ki * Kj : dn * Kj * Ki;
+            keep = !(est < p.fock_precision);
+          }
         }
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -259,7 +265,12 @@ __global__ void screen_kernel(const ScreenParams p) {
         base = __shfl_sync(0xffffffffu, base, 0);
         if (keep) {
           const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
-          if (pos < p.cap) p.tasks[pos] = make_int2(i, (int)j);
+          // engine precision of this quartet (hartree-fock++.cc:1693-1695), as its logarithm:
+          // the class kernels compare it with the primitive-pair screening sums
+          const double lnp = dn != 0.0 ? log(p.fock_precision / dn) : p.ln_needed_engine_precision;
+          if (pos < p.cap)
+            p.tasks[pos] = make_int4(i, (int)(j | ((unsigned)code << 30)), __double2loint(lnp),
+                                     __double2hiint(lnp));
         }
       }
     }
@@ -351,6 +362,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
     auto& a = kv.second.first;
     auto& b = kv.second.second;
     const int n = (int)a.size();
+    if (a.size() >= (size_t)1 << 30) { rc = LB200_ERR_INVALID; break; }   // task records keep 30 bits per pair index
     // shell-level Schwarz bound, no primitive screening (hartree-fock++.cc:1244-1247)
     lb200_pairs* all = nullptr;
     rc = build_pairs(ctx, obs, obs, n, a.data(), b.data(), kScreenOriginal,
@@ -463,7 +475,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   const long long cap = 1ll << 24;
   if (f->task_cap < cap) {
     cudaFree(f->d_tasks);
-    if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks, cap * sizeof(int2)), "cudaMalloc(tasks)")))
+    if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks, cap * sizeof(int4)), "cudaMalloc(tasks)")))
       return rc;
     f->task_cap = cap;
   }
@@ -528,6 +540,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           sp.Dnorm = f->d_Dnorm; sp.nshell = ns;
           sp.bra_dn = B.d_dn; sp.ket_dn = Kt.d_dn;
           sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
+          sp.ln_needed_engine_precision = std::log(needed_engine_precision);
           sp.rank = rank; sp.nranks = nranks;
           sp.tasks = f->d_tasks; sp.count = f->d_count; sp.cap = (unsigned)cap;
           cudaMemsetAsync(f->d_count, 0, 8, st);
@@ -545,7 +558,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           ++ctx->launches;
           EriParams p{};
           p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
-          p.tasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
+          p.tasks = nullptr; p.ftasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
           p.work_counter = f->d_count + 1;
           // uncontracted x uncontracted bucket: the pipelined kernel (LB200_NO_PRIM_KERNEL=1: A/B)
           static const bool no_prim = std::getenv("LB200_NO_PRIM_KERNEL") != nullptr;

@@ -50,7 +50,11 @@ enum EriMode : int { kModeStoreCart = 0, kModeStore = 1, kModeFock = 2 };
 
 struct EriParams {
   PairBlock bra, ket;        // kernel-internal orientation: bra = "lane side"
-  const int2* tasks;         // (bra pair, ket pair) indices
+  const int2* tasks;         // (bra pair, ket pair) indices (store modes)
+  // Fock mode: one 16-byte record per surviving quartet, written by the screening kernel:
+  // x = bra pair, y = ket pair | degeneracy code << 30 (deg = 1 << code, hartree-fock++.cc:1683-1687),
+  // (z, w) = ln of the engine precision of this quartet (hartree-fock++.cc:1693-1695) as a double
+  const int4* ftasks;
   const unsigned* ntasks_dev;  // if non-null, task count is read from device memory
   unsigned ntasks;
   int swap_tasks;             // 1: tasks are (ket pair, bra pair) in kernel orientation
