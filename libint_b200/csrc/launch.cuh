@@ -101,7 +101,10 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
         // (ps| row classes (5-15 %); with more rows per quartet the digestion's shared-memory and
         // register footprint costs more than the hidden latency gains, so those stay general
         if constexpr (MODE == kModeFock) {
-          if constexpr (RR<LC, LD, LA, LB>::NEC <= 4)
+#ifndef LB200_FOCK_PRIM_MAXNEC
+#define LB200_FOCK_PRIM_MAXNEC 4
+#endif
+          if constexpr (RR<LC, LD, LA, LB>::NEC <= LB200_FOCK_PRIM_MAXNEC)
             return launch_rowreg_prim_tr<LC, LD, LA, LB, false, true>(q, rows, num_sms, stream);
         } else {
           return launch_rowreg_prim<LC, LD, LA, LB>(q, rows, num_sms, stream);
