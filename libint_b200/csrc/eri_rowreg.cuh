@@ -245,7 +245,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   using K = RRK<LA, LB, LC, LD>;
   constexpr bool FOCK = (MODE == kModeFock);
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
-  constexpr int QSIZE = K::qsize(FOCK), THREADS = K::THREADS;
+  constexpr int QSIZE = K::qsize(FOCK);
   constexpr bool WL = K::WL;
   constexpr int GROUP = K::GROUP, QPG = K::QPG, NG = K::NG;
   static_assert(FMAX <= 6, "register pyramid is written for LC+LD <= 6");
