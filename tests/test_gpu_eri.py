@@ -258,3 +258,46 @@ def test_boys_branches_through_ss(ctx, oracle):
             got = _batch_one(ctx, capi, table)
             ref = oracle.compute2(oracle.Shells(*table, raw=False), precision=0.0).ravel()
             assert_parity(got, ref, "boys x=%g class %s" % (x, m_cl))
+
+
+def test_uncontracted_pipeline_ragged(ctx, oracle):
+    """The pipelined uncontracted kernel (eri_rowreg_prim.cuh) on ragged input: batches that are not
+    a multiple of the quartets per CTA (1, 2, 7, 1001 tasks), pairs whose only primitive pair is
+    screened out by ShellPair::init, quartets dropped by the primitive screen at a finite engine
+    precision, both output orientations -- against the reference Engine with the same precision."""
+    from libint_b200 import capi
+    rng = np.random.default_rng(2024)
+    nsh = 12
+    for cl in [(1, 0, 1, 0), (1, 1, 1, 1), (2, 1, 2, 0), (2, 2, 2, 1), (2, 2, 2, 2), (3, 2, 1, 0), (3, 3, 2, 1)]:
+        la, lb, lc, ld = cl
+        ls = [la] * nsh + [lb] * nsh + [lc] * nsh + [ld] * nsh
+        table = random_shell_table(rng, ls, 1, spread=4.0, amin=0.3, amax=12.0)
+        l, pure, nprim, O, al, co = table
+        O[1] = O[0] + np.array([9.0, 0, 0])          # a far, tight pair: nothing survives ShellPair::init
+        O[nsh + 1] = O[0] + np.array([-9.0, 0, 0])
+        al[1] = al[nsh + 1] = 11.0
+        eps = 1e-9
+        bs = capi.Basis(ctx, l, pure, nprim, O, al, co)
+        i = np.arange(nsh, dtype=np.int32)
+        bra = capi.Pairs(ctx, bs, bs, i, nsh + i, ln_prec=np.log(eps))
+        ket = capi.Pairs(ctx, bs, bs, 2 * nsh + i, 3 * nsh + i, ln_prec=np.log(eps))
+        assert bra.nprimpair < nsh                       # the far pair kept no primitive
+        osh = oracle.Shells(*table, raw=False)
+        blk = nc(la) * nc(lb) * nc(lc) * nc(ld)
+        for ntask in (1, 2, 7, 1001):
+            tasks = rng.integers(0, nsh, (ntask, 2)).astype(np.int32)
+            tasks[0] = (1, 3)                            # the empty pair is always present
+            got = capi.eri_batch(ctx, bra, ket, tasks, precision=eps)
+            swapped = capi.eri_batch(ctx, ket, bra, tasks[:, ::-1].copy(), precision=eps)
+            assert np.all(got[0] == 0.0)
+            nzero = 0
+            for t in range(min(ntask, 25)):
+                b, k = tasks[t]
+                ref = oracle.compute2(osh.subset([b, nsh + b, 2 * nsh + k, 3 * nsh + k]), precision=eps)
+                ref = np.zeros(blk) if ref is None else ref.ravel()
+                nzero += int(not ref.any())
+                amp = hrr_amplification(cl, O[[b, nsh + b, 2 * nsh + k, 3 * nsh + k]])
+                assert_parity(got[t], ref, "ragged %s n=%d task %d" % (cl, ntask, t), atol=ATOL * amp)
+                sw = swapped[t].reshape(nc(lc) * nc(ld), nc(la) * nc(lb)).T.ravel()
+                assert_parity(sw, ref, "ragged swapped %s n=%d task %d" % (cl, ntask, t), atol=ATOL * amp * 7.0 ** (lb + ld))
+            assert nzero >= 1
