@@ -500,14 +500,13 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
       // K_i * K_j * Dmax >= precision is necessary for survival
       jmax.assign(nb, (unsigned)nk);
       if (use_schwarz) {
+        // both bound lists are sorted descending, so the prefix length only shrinks from one bra
+        // row to the next: one sweep over (rows + kets) instead of a binary search per row (the
+        // host loop must stay ahead of eight GPUs' worth of class kernels)
+        int lo = nk;   // first j with schwarz[j] < thr
         for (int i = 0; i < nb; ++i) {
           const double thr = fock_precision / (Dmax * B.schwarz[i]) * (1.0 - 1e-12);
-          // first j with schwarz[j] < thr  (descending order)
-          int lo = 0, hi = nk;
-          while (lo < hi) {
-            const int mid = (lo + hi) / 2;
-            if (Kt.schwarz[mid] >= thr) lo = mid + 1; else hi = mid;
-          }
+          while (lo > 0 && Kt.schwarz[lo - 1] < thr) --lo;
           jmax[i] = (unsigned)lo;
         }
       }
