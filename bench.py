@@ -510,7 +510,7 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
                         % (nx * ny * nz, args.fock_basis, args.fock_precision),
             "nshell": len(obs), "nbf": n, "significant_pairs": int(len(f.pair_s1)),
             "shell_quartets": nquart, "seconds": sec, "e2e_seconds": e2e_sec,
-            "quartets_per_s": nquart / sec, "setup_seconds": setup_s, "n_gpus": world,
+            "quartets_per_s": nquart / sec, "setup_seconds": setup_s, "n_gpus": world, "scaling": "strong",
             "allreduce": "nccl sum of nbf^2 f64" if world > 1 else None,
             "checksum": float(Gh.abs().sum().item())}
 
