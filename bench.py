@@ -140,9 +140,11 @@ def reference_arm(args):
     vals = []
     for _ in range(args.warmup):
         cpu_sweep(classes, args.npairs, 2.0, ncores)
+    # a step = one bounded sample of the sweep; the whole run stays within ~2 minutes of CPU work
+    per_step = min(args.cpu_seconds, 120.0 / max(1, args.steps))
     t0 = time.time()
     for _ in range(args.steps):
-        mix, per, sample = cpu_sweep(classes, args.npairs, args.cpu_seconds, ncores)
+        mix, per, sample = cpu_sweep(classes, args.npairs, per_step, ncores)
         vals.append(mix)
     wall = time.time() - t0
     v = float(np.mean(vals))
