@@ -512,8 +512,10 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       // ---- hand the rows over to (quartet, cd) lanes ------------------------------------
       // (the K loop ended with a barrier, or had no shared traffic: the region is free)
       constexpr int TBOFF = K::OFF_B2;
-      if (valid && rmeta.row == 0) {
-        Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+      if constexpr (LB > 0) {   // A - B is only needed by the bra HRR
+        if (valid && rmeta.row == 0) {
+          Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+        }
       }
       if constexpr (LB > 0) {
         if (valid && rmeta.row >= K::ROW0)

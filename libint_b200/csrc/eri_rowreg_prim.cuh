@@ -187,7 +187,8 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           if (c < 6) cp_async16(S + K::S_BP + 2 * c, gb + 16 * c);
           else cp_async16(S + K::S_KP + 2 * (c - 6), gk + 16 * (c - 6));
         } else if (c < 15) {
-          cp_async8(S + K::S_AB + (c - 12), p.bra.AB + 3 * o.ib + (c - 12));
+          if constexpr (LB > 0)   // A - B is only needed by the bra HRR
+            cp_async8(S + K::S_AB + (c - 12), p.bra.AB + 3 * o.ib + (c - 12));
         } else {
           cp_async8(S + K::S_CD + (c - 15), p.ket.AB + 3 * o.ik + (c - 15));
         }

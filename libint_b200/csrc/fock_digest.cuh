@@ -91,8 +91,9 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
     else
       return fin_at(a * nb + b, c * nd + d);
   };
-  const int bfa = p.bra.bf[2 * ib], bfb = p.bra.bf[2 * ib + 1];
-  const int bfc = p.ket.bf[2 * ik], bfd = p.ket.bf[2 * ik + 1];
+  const int2 bf_ab = reinterpret_cast<const int2*>(p.bra.bf)[ib];   // one 8-byte load per pair
+  const int2 bf_cd = reinterpret_cast<const int2*>(p.ket.bf)[ik];
+  const int bfa = bf_ab.x, bfb = bf_ab.y, bfc = bf_cd.x, bfd = bf_cd.y;
   const int n = p.nbf;
   const double* __restrict__ D = p.D;
   double* __restrict__ F = p.F;
