@@ -133,3 +133,30 @@ def test_gpu_scf_config1_h2o_ccpvdz(ctx, oracle):
     for a, c in zip(s_gpu.history, s_cpu.history):
         assert abs(a[1] - c[1]) < 1e-9
     assert -76.0 < e_gpu < -75.98   # RHF/cc-pVDZ at h2o.xyz's stretched geometry (r_OH = 1.10 A)
+
+
+@pytest.mark.gpu
+def test_hartree_fock_cli_output_is_parsed_by_the_reference_validators(tmp_path):
+    """`python -m libint_b200.hartree_fock` prints what hartree-fock-validate.py:19-24 and
+    hartree-fock++-validate.py:60-70 look for; the regex and tolerances below are theirs."""
+    import os
+    import re
+    import subprocess
+    import sys
+    from libint_b200 import basis as b
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xyz = tmp_path / "h2o_rotated.xyz"
+    xyz.write_text("3\nrotated water\n" + "".join(
+        "%s %.17g %.17g %.17g\n" % ({8: "O", 1: "H"}[Z], *r) for Z, r in b.H2O_ROTATED_XYZ_ANGSTROM))
+    cases = [(["--codata2010", str(tmp_path / "h2o.xyz"), "sto-3g"], -74.942080057696, 1e-11),
+             ([str(xyz), "aug-cc-pVDZ"], -76.003354058439, 5e-12)]
+    (tmp_path / "h2o.xyz").write_text("3\n\n" + "".join(
+        "%s %.5f %.5f %.5f\n" % ({8: "O", 1: "H"}[Z], *r) for Z, r in b.H2O_XYZ_ANGSTROM))
+    for argv, eref, tol in cases:
+        r = subprocess.run([sys.executable, "-m", "libint_b200.hartree_fock"] + argv, capture_output=True,
+                           text=True, cwd=root, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        found = [re.match(r"\*\* Hartree-Fock energy =\s*([-\d.]+)", ln) for ln in r.stdout.splitlines()]
+        found = [m for m in found if m]
+        assert len(found) == 1
+        assert abs(eref - float(found[0].group(1))) < tol
