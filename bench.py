@@ -382,6 +382,7 @@ def main():
             "per_class": per, "fock": fock, "df3c": df3c}
 
     if rank == 0 and not args.no_cpu_baseline:
+        line["parity"] = sweep_parity(ctx, work, args.npairs)
         ncores = os.cpu_count() or 1
         mix, cper, sample = cpu_sweep(classes, args.npairs, args.cpu_seconds, ncores)
         line["cpu_baseline"] = {"value": mix, "unit": UNIT, "cores": ncores, "kind": "port",
@@ -391,6 +392,38 @@ def main():
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def sweep_parity(ctx, work, npairs, per_class=48):
+    """BASELINE configs[1]'s tolerance check on the sweep's own inputs: the first quartets of every
+    class through lb200_eri_batch against the reference Engine (oracle), 1e-12 relative / 1e-14
+    absolute, the absolute part scaled by the HRR conditioning (1+|AB|)^lb (1+|CD|)^ld of the
+    shell set as in tests/util.py (tests/eri/test.cc:77-83 notes the same loss in the reference)."""
+    from libint_b200 import capi
+    from oracle import pyoracle as po
+    nbad = nchk = 0
+    max_abs = max_rel = 0.0
+    for w in work:
+        t = w["tasks"][:per_class].cpu().numpy()
+        got = capi.eri_batch(ctx, w["bra"], w["ket"], t)
+        sh = po.Shells(*w["tab"], raw=False)
+        O = np.asarray(w["tab"][3])
+        cl = w["cl"]
+        for q, (b, k) in enumerate(t):
+            idx = [int(b), npairs + int(b), 2 * npairs + int(k), 3 * npairs + int(k)]
+            ref = po.compute2(sh.subset(idx), precision=0.0).ravel()
+            amp = (1.0 + np.linalg.norm(O[idx[0]] - O[idx[1]])) ** min(cl[0], cl[1]) * \
+                  (1.0 + np.linalg.norm(O[idx[2]] - O[idx[3]])) ** min(cl[2], cl[3])
+            err = np.abs(got[q] - ref)
+            nbad += int(np.sum(err > 1e-12 * np.abs(ref) + 1e-14 * amp))
+            nchk += err.size
+            max_abs = max(max_abs, float(err.max()))
+            big = np.abs(ref) > 1e-3 * np.abs(ref).max()   # elements that are not cancellation residues
+            if big.any():
+                max_rel = max(max_rel, float((err[big] / np.abs(ref[big])).max()))
+    return {"integrals_checked": nchk, "outside_tolerance": nbad, "max_abs_err": max_abs,
+            "max_rel_err_significant": max_rel, "quartets_per_class": per_class,
+            "tolerance": "1e-12 rel + 1e-14 abs x HRR conditioning", "against": "reference Engine (oracle)"}
 
 
 def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world):
