@@ -160,3 +160,17 @@ def test_hartree_fock_cli_output_is_parsed_by_the_reference_validators(tmp_path)
         found = [m for m in found if m]
         assert len(found) == 1
         assert abs(eref - float(found[0].group(1))) < tol
+
+
+def test_hartree_fock_cli_fails_loudly_without_gpu():
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "libint_b200.hartree_fock", "--codata2010"], capture_output=True,
+                       text=True, cwd=root, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    assert "Hartree-Fock energy" not in r.stdout
