@@ -398,6 +398,8 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
   });
   std::vector<int> ssz(ns);
   for (int s = 0; s < ns; ++s) ssz[s] = obs->size(s);
+  // per-device attribute: set for this context's device whenever a builder is created
+  cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaMalloc(&f->d_shell2bf, ns * sizeof(int));
   cudaMalloc(&f->d_shellsize, ns * sizeof(int));
   cudaMalloc(&f->d_Dnorm, (size_t)ns * ns * 8);
@@ -547,11 +549,6 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           const size_t row_bytes = 2 * (size_t)ns * sizeof(double);
           sp.stage_rows = row_bytes <= (size_t)96 * 1024;
           const size_t smem = sp.stage_rows ? row_bytes : 0;
-          static bool attr_set = false;
-          if (!attr_set) {
-            cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_set = true;
-          }
           const int grid = std::min(ctx->num_sms * 16, sp.nrow);
           screen_kernel<<<grid, threads, smem, st>>>(sp);
           ++ctx->launches;
@@ -565,6 +562,8 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.boys = ctx->d_boys;
           p.screening = kScreenSchwarzInf;
           p.D = f->d_D; p.F = f->d_F; p.nbf = n; p.Dnorm = f->d_Dnorm; p.nshell = ns;
+          p.sph_rowptr = ctx->d_sph_rowptr; p.sph_col = ctx->d_sph_col;
+          p.sph_val = ctx->d_sph_val; p.sph_base = ctx->d_sph_base;
           p.fock_precision = fock_precision;
           p.needed_engine_precision = needed_engine_precision;
           p.ln_needed_engine_precision = std::log(needed_engine_precision);

@@ -11,6 +11,105 @@
 
 namespace lb200 {
 
+// Run-time purity path.  The compile-time digestion below is specialised for the standard
+// convention (pure iff l >= 2, what BasisSet gives cc-pVXZ / def2 bases); a block whose shells
+// deviate -- Cartesian d of 6-31G* (basis.h.in:368-386), BasisSet::set_pure(false), a pure p
+// shell -- takes this generic routine: densify, one sparse pass per pure index
+// (solidharmonics.h:281-463 in the order of engine.impl.h:1965-1985), then the same six
+// contractions with run-time block sizes.  One non-inlined copy serves every class kernel.
+struct GenericDigest {
+  const double* D;
+  double* F;
+  int nbf;
+  const int *rowptr, *col, *base;
+  const double* val;
+  int l[4], pure[4], bf[4];
+};
+
+static __device__ __noinline__ void fock_digest_generic(const GenericDigest g, bool active, int lane, int T,
+                                                 bool warp_sync, double* __restrict__ fin, int CS,
+                                                 double* __restrict__ buf2, double deg) {
+  constexpr int RP = 2 * kMaxShellL + 2;
+  int n[4] = {nc(g.l[0]), nc(g.l[1]), nc(g.l[2]), nc(g.l[3])};
+  {
+    const int NCD = n[2] * n[3], NAB = n[0] * n[1];
+    if (active)
+      for (int i = lane; i < NAB * NCD; i += T) buf2[i] = fin[(i / NCD) * CS + i % NCD];
+    if (warp_sync) __syncwarp(); else __syncthreads();
+  }
+  double* cur = buf2;
+  double* oth = fin;
+  for (int ax = 0; ax < 4; ++ax) {
+    if (!(g.pure[ax] && g.l[ax] > 0)) continue;
+    const int L = g.l[ax], np = 2 * L + 1, nin = n[ax];
+    int outer = 1, inner = 1;
+    for (int x = 0; x < ax; ++x) outer *= n[x];
+    for (int x = ax + 1; x < 4; ++x) inner *= n[x];
+    const int b0 = g.base[L];
+    if (active)
+      for (int i = lane; i < outer * np * inner; i += T) {
+        const int o = i / (np * inner), r = i - o * np * inner;
+        const int m = r / inner, in = r - m * inner;
+        double acc = 0.0;
+        for (int k = g.rowptr[L * RP + m]; k < g.rowptr[L * RP + m + 1]; ++k)
+          acc += g.val[b0 + k] * cur[(o * nin + g.col[b0 + k]) * inner + in];
+        oth[i] = acc;
+      }
+    if (warp_sync) __syncwarp(); else __syncthreads();
+    double* t = cur; cur = oth; oth = t;
+    n[ax] = np;
+  }
+  if (!active) return;
+  const int na = n[0], nb = n[1], nc_ = n[2], nd = n[3], nbf = g.nbf;
+  const int bfa = g.bf[0], bfb = g.bf[1], bfc = g.bf[2], bfd = g.bf[3];
+  auto I = [&](int a, int b, int c, int d) -> double { return cur[((a * nb + b) * nc_ + c) * nd + d]; };
+  const double* __restrict__ D = g.D;
+  double* __restrict__ F = g.F;
+  const double kdeg = -0.25 * deg;
+  for (int i = lane; i < na * nb; i += T) {  // F(a,b) += D(c,d) v
+    const int a = i / nb, b = i - a * nb;
+    double s = 0.0;
+    for (int c = 0; c < nc_; ++c)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * D[(bfc + c) * nbf + bfd + d];
+    atomicAdd(&F[(bfa + a) * nbf + bfb + b], s * deg);
+  }
+  for (int i = lane; i < nc_ * nd; i += T) {  // F(c,d) += D(a,b) v
+    const int c = i / nd, d = i - c * nd;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * D[(bfa + a) * nbf + bfb + b];
+    atomicAdd(&F[(bfc + c) * nbf + bfd + d], s * deg);
+  }
+  for (int i = lane; i < na * nc_; i += T) {  // F(a,c) -= 1/4 D(b,d) v
+    const int a = i / nc_, c = i - a * nc_;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * D[(bfb + b) * nbf + bfd + d];
+    atomicAdd(&F[(bfa + a) * nbf + bfc + c], s * kdeg);
+  }
+  for (int i = lane; i < nb * nd; i += T) {  // F(b,d) -= 1/4 D(a,c) v
+    const int b = i / nd, d = i - b * nd;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * D[(bfa + a) * nbf + bfc + c];
+    atomicAdd(&F[(bfb + b) * nbf + bfd + d], s * kdeg);
+  }
+  for (int i = lane; i < na * nd; i += T) {  // F(a,d) -= 1/4 D(b,c) v
+    const int a = i / nd, d = i - a * nd;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b)
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * D[(bfb + b) * nbf + bfc + c];
+    atomicAdd(&F[(bfa + a) * nbf + bfd + d], s * kdeg);
+  }
+  for (int i = lane; i < nb * nc_; i += T) {  // F(b,c) -= 1/4 D(a,d) v
+    const int b = i / nc_, c = i - b * nc_;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a)
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * D[(bfa + a) * nbf + bfd + d];
+    atomicAdd(&F[(bfb + b) * nbf + bfc + c], s * kdeg);
+  }
+}
+
 template <int LA, int LB, int LC, int LD, int T, bool WARP_SYNC>
 __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int lane,
                                             double* __restrict__ fin /* [NAB][CS] */, int,
@@ -21,6 +120,26 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
   constexpr int na = PA_ ? npure(LA) : NA, nb = PB_ ? npure(LB) : NB;
   constexpr int nc_ = PC_ ? npure(LC) : NC, nd = PD_ ? npure(LD) : ND;
   constexpr int NPASS = PA_ + PB_ + PC_ + PD_;
+  {
+    // grid-uniform: all pairs of a block share one purity pattern (PairBlock)
+    auto std_ok = [](int l, int pure) { return l == 0 || (pure != 0) == (l >= 2); };
+    if (!(std_ok(LA, p.bra.pure_a) && std_ok(LB, p.bra.pure_b) && std_ok(LC, p.ket.pure_a) &&
+          std_ok(LD, p.ket.pure_b))) {
+      GenericDigest g;
+      g.D = p.D; g.F = p.F; g.nbf = p.nbf;
+      g.rowptr = p.sph_rowptr; g.col = p.sph_col; g.base = p.sph_base; g.val = p.sph_val;
+      g.l[0] = LA; g.l[1] = LB; g.l[2] = LC; g.l[3] = LD;
+      g.pure[0] = p.bra.pure_a; g.pure[1] = p.bra.pure_b; g.pure[2] = p.ket.pure_a; g.pure[3] = p.ket.pure_b;
+      g.bf[0] = g.bf[1] = g.bf[2] = g.bf[3] = 0;
+      if (active) {
+        const int2 ab = reinterpret_cast<const int2*>(p.bra.bf)[ib];
+        const int2 cd = reinterpret_cast<const int2*>(p.ket.bf)[ik];
+        g.bf[0] = ab.x; g.bf[1] = ab.y; g.bf[2] = cd.x; g.bf[3] = cd.y;
+      }
+      fock_digest_generic(g, active, lane, T, WARP_SYNC, fin, CS, buf2, deg);
+      return;
+    }
+  }
   auto fin_at = [&](int ab, int cd) -> double { return fin[ab * CS + cd]; };
   auto sync = [] {
     if constexpr (WARP_SYNC) __syncwarp(); else __syncthreads();

@@ -9,6 +9,27 @@
 namespace lb200 {
 
 constexpr int kSmemLimit = 227 * 1024;  // usable dynamic shared memory per CTA on sm_100
+constexpr int kMaxDevices = 64;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute and the occupancy depends
+// on the device: both are set / queried once per (kernel, current device), not once per process
+template <class Kern>
+cudaError_t kernel_ctas_per_sm(Kern kern, int threads, int smem, int* cache, int* out) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (cache[dev] == 0) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    int nb = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
+    if (err != cudaSuccess) return err;
+    cache[dev] = nb < 1 ? 1 : nb;
+  }
+  *out = cache[dev];
+  return cudaSuccess;
+}
 
 template <int LA, int LB, int LC, int LD, int MODE>
 cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
@@ -17,15 +38,10 @@ cudaError_t launch_rowreg(const EriParams& p, const RowInfo* rows, int num_sms,
   constexpr int SMEM = K::QPC * K::qsize(MODE == kModeFock) * 8;
   static_assert(SMEM <= kSmemLimit, "row-register kernel exceeds shared memory");
   auto kern = eri_rowreg_kernel<LA, LB, LC, LD, MODE>;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (err != cudaSuccess) return err;
-    int nb = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::THREADS, SMEM);
-    if (err != cudaSuccess) return err;
-    ctas_per_sm = nb < 1 ? 1 : nb;
-  }
+  // the shared-memory opt-in and the occupancy are per device: cache them per device ordinal
+  static int cache[kMaxDevices] = {};
+  int ctas_per_sm = 0;
+  if (cudaError_t err = kernel_ctas_per_sm(kern, K::THREADS, SMEM, cache, &ctas_per_sm)) return err;
   long long grid = (long long)num_sms * ctas_per_sm;
   if (!p.ntasks_dev) {
     const long long need = ((long long)p.ntasks + K::QPC - 1) / K::QPC;
@@ -44,15 +60,10 @@ cudaError_t launch_rowreg_prim_tr(const EriParams& p, const RowInfo* rows, int n
   constexpr int SMEM = K::QPC * K::QSIZE * 8;
   static_assert(SMEM <= kSmemLimit, "pipelined row-register kernel exceeds shared memory");
   auto kern = eri_rowreg_prim_kernel<LA, LB, LC, LD, TR, FOCK>;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (err != cudaSuccess) return err;
-    int nb = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::THREADS, SMEM);
-    if (err != cudaSuccess) return err;
-    ctas_per_sm = nb < 1 ? 1 : nb;
-  }
+  // the shared-memory opt-in and the occupancy are per device: cache them per device ordinal
+  static int cache[kMaxDevices] = {};
+  int ctas_per_sm = 0;
+  if (cudaError_t err = kernel_ctas_per_sm(kern, K::THREADS, SMEM, cache, &ctas_per_sm)) return err;
   long long grid = (long long)num_sms * ctas_per_sm;
   if (!p.ntasks_dev) {
     const long long need = ((long long)p.ntasks + K::QPC - 1) / K::QPC;

@@ -78,6 +78,11 @@ struct EriParams {
   double fock_precision;
   double ln_needed_engine_precision;
   double needed_engine_precision;
+  // sparse cart->pure tables (context.cu) for the run-time purity path of the Fock digestion
+  const int* sph_rowptr;     // [(kMaxShellL+1)][2*kMaxShellL+2]
+  const int* sph_col;
+  const double* sph_val;
+  const int* sph_base;       // [(kMaxShellL+1)]
 };
 
 }  // namespace lb200

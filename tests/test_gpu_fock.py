@@ -143,3 +143,52 @@ def test_device_buffers_and_linearity(ctx):
     Gt = fb(torch.from_numpy(D1).cuda(), precision=1e-14, use_schwarz=False)
     assert Gt.is_cuda and Gt.dtype == torch.float64
     assert_parity(Gt.cpu().numpy(), G1, "device buffers", rtol=1e-12, atol=2e-14)
+
+
+def _purity_case(ctx, oracle, bs, what):
+    from libint_b200 import capi
+    B = capi.Basis(ctx, *bs.flat())
+    assert B.nbf == bs.nbf
+    f = capi.Fock(ctx, B)
+    of = oracle.Fock(oracle.Shells(*bs.flat(), raw=False), f.pair_s1, f.pair_s2, nthreads=4)
+    D = _sym_density(bs.nbf, seed=3, scale=0.2)
+    G, st = f.build(D, 1e-12, stats=True)
+    Gref, ost = of.build(D, 1e-12)
+    assert st["nquartets"] == ost["nquartets"]
+    np.testing.assert_allclose(f.schwarz(), of.schwarz(), rtol=1e-12, atol=1e-15)
+    assert_parity(G, Gref, what, rtol=1e-12, atol=2e-14)
+    assert np.array_equal(G, G.T)
+
+
+def test_fock_cartesian_d_basis(ctx, oracle):
+    """6-31G* keeps Cartesian d shells (Gaussian convention, basis.h.in:368-386): the digestion
+    must honour the per-shell purity flag, not assume pure-iff-l>=2 (engine.impl.h:1965-1985)."""
+    bs = _h2o("6-31g*")
+    assert any(s.l == 2 and not s.pure for s in bs)
+    _purity_case(ctx, oracle, bs, "G H2O/6-31G* (Cartesian d)")
+
+
+def test_fock_set_pure_false(ctx, oracle):
+    """BasisSet::set_pure(false) (basis.h.in:165-171) on cc-pVDZ: every shell Cartesian."""
+    bs = _h2o("cc-pvdz")
+    bs.set_pure(False)
+    assert bs.nbf == 25
+    _purity_case(ctx, oracle, bs, "G H2O/cc-pVDZ set_pure(false)")
+
+
+def test_fock_pure_p_shell_and_mixed(ctx, oracle):
+    """set_pure(true) makes the p shells solid harmonics too (order y,z,x, solidharmonics.h:114-174);
+    then a mixed pattern: one Cartesian d next to pure ones."""
+    bs = _h2o("cc-pvdz")
+    bs.set_pure(True)
+    _purity_case(ctx, oracle, bs, "G H2O/cc-pVDZ set_pure(true)")
+    from libint_b200.basis import Atom, H2O_XYZ_ANGSTROM, atoms_from_tuples, BasisSet
+    a = atoms_from_tuples(H2O_XYZ_ANGSTROM)
+    atoms = a + [Atom(x.atomic_number, x.x + 3.1, x.y + 0.4, x.z - 0.2) for x in a]
+    bs = BasisSet("cc-pvdz", atoms)
+    flip = [i for i, s in enumerate(bs) if s.l == 2][0]
+    bs[flip].pure = False
+    first_p = [i for i, s in enumerate(bs) if s.l == 1][0]
+    bs[first_p].pure = True
+    bs._refresh()
+    _purity_case(ctx, oracle, bs, "G (H2O)2/cc-pVDZ mixed purity")
