@@ -119,6 +119,24 @@ int lb200_eri_class_supported(int la, int lb, int lc, int ld);
 /* doubles per task written by lb200_eri_batch */
 long long lb200_eri_block_size(const lb200_pairs* bra, const lb200_pairs* ket, int pure_out);
 
+/* ---- the reference's innermost plugin call, batched: libint2_build_eri[la][lb][lc][ld](Libint_t*)
+ *      (src/bin/libint/iface.cc:114-185, used at include/libint2/engine.impl.h:1898-1899).  The
+ *      caller supplies the per-primitive prerequisites Engine::compute2 writes into Libint_t
+ *      (engine.impl.h:1514-1641), in its own bra/ket orientation; VRR, contraction and HRR run on
+ *      the GPU.  Class (la lb|lc ld) with la >= lb, lc >= ld, either bra/ket order.
+ *        prim_off[ntasks+1]  records of shell set t are [prim_off[t], prim_off[t+1])  (contrdepth)
+ *        recs                LB200_PREREQ_DOUBLES doubles per primitive quartet:
+ *                            (ss|ss)^(m) m = 0..24 | PA[3] | QC[3] | WP[3] | WQ[3] |
+ *                            oo2z oo2e oo2ze roz roe      (PA = 0 for a unit-shell bra2: 3eri/2eri)
+ *        geom[ntasks][6]     AB[3] = A - B, CD[3] = C - D
+ *        out[ntasks][ncart(la) ncart(lb) ncart(lc) ncart(ld)]   row-major, Cartesian
+ *      Host buffers; synchronous.  include/libint2_b200_iface (liblibint_b200_iface.so) wraps this
+ *      into the Libint_t / libint2_build_* ABI itself. */
+#define LB200_PREREQ_DOUBLES 42
+int lb200_eri_prereq_batch(lb200_context* ctx, int la, int lb, int lc, int ld, long long ntasks,
+                           const int* prim_off, const double* recs, const double* geom,
+                           double* out);
+
 /* ---- direct Fock build: compute_2body_fock (hartree-fock++.cc:1574-1772).
  *      pairs (s1 >= s2) = the significant shell-pair list obs_shellpair_list
  *      (hartree-fock++.cc:1305-1381); lb200_significant_pairs computes it.
@@ -145,6 +163,15 @@ int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks);
 int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double precision,
                      int use_schwarz, int rank, int nranks, double* G, int G_on_device,
                      double* stats);
+
+/* Profiling of the build (no reference counterpart): with profiling on, every (bra class, ket class,
+ * contraction buckets) launch of the next builds is timed with CUDA events (one stream sync per
+ * launch: diagnostics, not for timed runs) and its surviving primitive quartets are counted in the
+ * kernel.  get_profile copies 9 doubles per row -- la, lb, lc, ld, bra bucket, ket bucket, device ms,
+ * shell quartets, surviving primitive quartets -- sorted by time; returns the row count (rows = NULL:
+ * count only).  bench.py derives the per-class FP64 roofline from it. */
+int lb200_fock_set_profile(lb200_fock* f, int on);
+long long lb200_fock_get_profile(const lb200_fock* f, double* rows, long long cap);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,27 @@ def build(jobs=None, force=False, verbose=False):
     if jobs_list or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets", "-lcudart_static"]
              if False else [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets"])
+    build_iface(force=bool(jobs_list) or force)
     return LIB
+
+
+IFACE_LIB = os.path.join(OUT, "liblibint_b200_iface%s.so" % SUFFIX)
+
+
+def build_iface(force=False):
+    """liblibint_b200_iface.so: the reference's Libint_t / libint2_build_* C boundary
+    (csrc/iface/libint2_b200_iface.cc, plain host C++) on top of the CUDA library."""
+    src = os.path.join(CSRC, "iface", "libint2_b200_iface.cc")
+    inc = os.path.join(HERE, "..", "include")
+    deps = glob.glob(os.path.join(inc, "libint2", "util", "generated", "*.h")) + \
+        [os.path.join(inc, "libint_b200.h")]
+    if force or _newer(src, IFACE_LIB, deps):
+        _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-fPIC", "-shared", "-I", inc, src, "-o", IFACE_LIB,
+              "-L", OUT, "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN", "-lpthread",
+              # link libstdc++ dynamically (this image's g++ wrapper otherwise finds only the static
+              # archive, and a second copy inside the .so clashes with the host process's)
+              "-L/usr/lib/gcc/x86_64-linux-gnu/13", "-Wl,--exclude-libs,ALL"])
+    return IFACE_LIB
 
 
 if __name__ == "__main__":

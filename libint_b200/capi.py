@@ -53,6 +53,7 @@ SIGNATURES = {
     "lb200_pairs_get": (C.c_int, [vp, C.c_int, dp, C.c_int]),
     "lb200_eri_batch": (C.c_int, [vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_double,
                                   C.c_int, vp, C.c_int]),
+    "lb200_eri_prereq_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, ip, dp, dp, dp]),
     "lb200_eri_block_size": (C.c_longlong, [vp, vp, C.c_int]),
     "lb200_eri_class_supported": (C.c_int, [C.c_int] * 4),
     "lb200_significant_pairs": (C.c_int, [vp, C.c_double, ip, ip, C.c_longlong,
@@ -60,6 +61,8 @@ SIGNATURES = {
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_fock_set_profile": (C.c_int, [vp, C.c_int]),
+    "lb200_fock_get_profile": (C.c_longlong, [vp, dp, C.c_longlong]),
     "lb200_fock_task_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "lb200_fp64_peak_probe": (C.c_int, [vp, C.c_int, dp, dp]),
     "lb200_fock_build": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp,
@@ -306,6 +309,17 @@ class Fock:
         if stats:
             return out, {"nquartets": st[0], "launches": st[1], "ms": st[2], "candidates": st[3]}
         return out
+
+    def set_profile(self, on=True):
+        load().lb200_fock_set_profile(self.h, int(bool(on)))
+
+    def profile(self):
+        """rows of the last profiled build: (la, lb, lc, ld, bra bucket, ket bucket, ms, quartets,
+        surviving primitive quartets), slowest first."""
+        n = load().lb200_fock_get_profile(self.h, None, 0)
+        rows = np.zeros((max(n, 1), 9))
+        load().lb200_fock_get_profile(self.h, _d(rows), n)
+        return rows[:n]
 
     def close(self):
         if self.h:

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(RR<LA, LB, LC, LD>::THREADS, RR<LA, LB, LC, LD
 eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   using K = RRK<LA, LB, LC, LD>;
   constexpr bool FOCK = (MODE == kModeFock);
+  constexpr bool PREREQ = (MODE == kModePrereq);
   constexpr int EMAX = K::EMAX, FMAX = K::FMAX, L = K::L, NEC = K::NEC, NECX = K::NECX;
   constexpr int QSIZE = K::qsize(FOCK);
   constexpr bool WL = K::WL;
@@ -325,8 +326,9 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     int ib = 0, ik = 0, pb0 = 0, nb = 0, pk0 = 0, nk = 0;
     double ln_prec = p.ln_precision, prec = p.precision, deg = 1.0;
     if (valid) {
-      int2 tk;
-      if constexpr (FOCK) {   // precision and degeneracy come with the task (screen_kernel)
+      int2 tk = make_int2(0, 0);
+      if constexpr (PREREQ) {
+      } else if constexpr (FOCK) {   // precision and degeneracy come with the task (screen_kernel)
         const int4 ft = p.ftasks[task];
         tk = make_int2(ft.x, ft.y & 0x3fffffff);
         deg = (double)(1 << ((unsigned)ft.y >> 30));
@@ -336,10 +338,17 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       }
       ib = p.swap_tasks ? tk.y : tk.x;
       ik = p.swap_tasks ? tk.x : tk.y;
-      pb0 = p.bra.prim_off[ib];
-      nb = p.bra.prim_off[ib + 1] - pb0;
-      pk0 = p.ket.prim_off[ik];
-      nk = p.ket.prim_off[ik + 1] - pk0;
+      if constexpr (PREREQ) {   // one run of caller-made records per task; no pair blocks
+        ib = ik = (int)task;
+        pb0 = p.prereq_off[task];
+        nb = p.prereq_off[task + 1] - pb0;
+        nk = 1;
+      } else {
+        pb0 = p.bra.prim_off[ib];
+        nb = p.bra.prim_off[ib + 1] - pb0;
+        pk0 = p.ket.prim_off[ik];
+        nk = p.ket.prim_off[ik + 1] - pk0;
+      }
     }
     const int nit = nb * nk;
     if constexpr (!WL) {
@@ -350,7 +359,12 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     double CD[3] = {0, 0, 0};
     if (valid) {
-      CD[0] = p.ket.AB[3 * ik]; CD[1] = p.ket.AB[3 * ik + 1]; CD[2] = p.ket.AB[3 * ik + 2];
+      if constexpr (PREREQ) {   // swap_tasks: this kernel's ket is the caller's bra
+        const double* gv = p.prereq_geom + 6 * (size_t)task + (p.swap_tasks ? 0 : 3);
+        CD[0] = gv[0]; CD[1] = gv[1]; CD[2] = gv[2];
+      } else {
+        CD[0] = p.ket.AB[3 * ik]; CD[1] = p.ket.AB[3 * ik + 1]; CD[2] = p.ket.AB[3 * ik + 2];
+      }
     }
     const double npbraket = (double)nb * (double)nk;
     double acc[K::NFT];
@@ -368,14 +382,16 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       bool on = valid && it < nit;
       PrimPair bp, kp;
       double pfac = 0.0, Targ = 0.0, rho = 0.0, oogpq = 0.0;
-      if (on) {
+      if constexpr (PREREQ) {
+      } else if (on) {
         const int ipb = it / nk;
         const int ipk = it - ipb * nk;
         bp = p.bra.prim[pb0 + ipb];
         kp = p.ket.prim[pk0 + ipk];
         on = bp.ln_scr + kp.ln_scr > ln_prec;  // engine.impl.h:1313-1314
       }
-      if (on) {
+      if constexpr (PREREQ) {
+      } else if (on) {
         const double PQx = bp.P[0] - kp.P[0], PQy = bp.P[1] - kp.P[1], PQz = bp.P[2] - kp.P[2];
         const double PQ2 = PQx * PQx + PQy * PQy + PQz * PQz;
         const double gpq = bp.gamma + kp.gamma;
@@ -391,7 +407,31 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         Targ = PQ2 * rho;
       }
       double PA[3], WP[3], QC[3], WQ[3], oo2z = 0, roz = 0, koo2e[6], roe = 0, ce[3];
-      if (on) {
+      if constexpr (PREREQ) {
+        if (on) {
+          ++nsurv;
+          const PrereqRec& r = p.prereq[pb0 + it];
+          const bool sw = p.swap_tasks != 0;   // kernel bra = caller ket
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            PA[d] = sw ? r.QC[d] : r.PA[d];
+            QC[d] = sw ? r.PA[d] : r.QC[d];
+            WP[d] = sw ? r.WQ[d] : r.WP[d];
+            WQ[d] = sw ? r.WP[d] : r.WQ[d];
+          }
+          oo2z = sw ? r.oo2e : r.oo2z;
+          roz = sw ? r.roe : r.roz;
+          const double oo2e = sw ? r.oo2z : r.oo2e;
+          koo2e[0] = 0.0; koo2e[1] = oo2e; koo2e[2] = 2.0 * oo2e; koo2e[3] = 3.0 * oo2e;
+          koo2e[4] = 4.0 * oo2e; koo2e[5] = 5.0 * oo2e;
+          roe = sw ? r.roz : r.roe;
+          ce[0] = rmeta.q[0] * r.oo2ze; ce[1] = rmeta.q[1] * r.oo2ze; ce[2] = rmeta.q[2] * r.oo2ze;
+        } else {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) PA[d] = WP[d] = QC[d] = WQ[d] = ce[d] = 0.0;
+          koo2e[0] = koo2e[1] = koo2e[2] = koo2e[3] = koo2e[4] = koo2e[5] = 0.0;
+        }
+      } else if (on) {
         ++nsurv;
         const double gp = oogpq * bp.gamma, gq = oogpq * kp.gamma;
 #pragma unroll
@@ -419,7 +459,12 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
       // ---- Boys: lanes m of the quartet, then broadcast through shared memory ----------
       double F[L + 1];
-      if constexpr (NEC == 1) {
+      if constexpr (PREREQ) {   // (ss|ss)^(m) come with the record; every lane reads its own copy
+        static_for<L + 1>([&](auto mc) {
+          constexpr int m = decltype(mc)::value;
+          F[m] = on ? p.prereq[pb0 + it].F[m] : 0.0;
+        });
+      } else if constexpr (NEC == 1) {
         static_for<L + 1>([&](auto mc) {
           constexpr int m = decltype(mc)::value;
           F[m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
@@ -506,6 +551,10 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     double H[K::NCD];
     rr_hrr_regs<LC, LD>(acc, CD, H);
     const bool screened_out = (nsurv == 0);
+    if constexpr (FOCK) {   // K_eff of the flop model, counted only when profiling
+      if (p.prim_counter && valid && rmeta.row == 0 && nsurv)
+        atomicAdd(p.prim_counter, (unsigned long long)nsurv);
+    }
     if (screened_out) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
 
     {
@@ -514,7 +563,12 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       constexpr int TBOFF = K::OFF_B2;
       if constexpr (LB > 0) {   // A - B is only needed by the bra HRR
         if (valid && rmeta.row == 0) {
-          Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+          if constexpr (PREREQ) {
+            const double* gv = p.prereq_geom + 6 * (size_t)task + (p.swap_tasks ? 3 : 0);
+            Q[0] = gv[0]; Q[1] = gv[1]; Q[2] = gv[2];
+          } else {
+            Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+          }
         }
       }
       if constexpr (LB > 0) {

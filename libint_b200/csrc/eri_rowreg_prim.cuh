@@ -376,6 +376,9 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
+    if constexpr (FOCK) {
+      if (p.prim_counter && valid && rmeta.row == 0 && on) atomicAdd(p.prim_counter, 1ull);
+    }
     sync();   // last cross-term reads done: the phase-2 areas alias the cross-term area
     constexpr int TBOFF = K::OFF_B2;
     if constexpr (LB > 0) {

@@ -51,6 +51,11 @@ struct lb200_fock {
   unsigned* d_count = nullptr;
   unsigned* d_jmax = nullptr;
   long long task_cap = 0, jmax_cap = 0;
+  // per (bra class, ket class) timings of the last build, filled when profiling is on
+  bool profile = false;
+  unsigned long long* d_primcount = nullptr;
+  struct ProfRow { int c[6]; double ms, nq, nprim; };
+  std::vector<ProfRow> prof;
 };
 
 namespace {
@@ -420,8 +425,28 @@ int lb200_fock_destroy(lb200_fock* f) {
   cudaFree(f->d_D); cudaFree(f->d_F); cudaFree(f->d_Dnorm); cudaFree(f->d_scalar);
   cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize); cudaFree(f->d_tasks); cudaFree(f->d_count);
   cudaFree(f->d_jmax);
+  cudaFree(f->d_primcount);
   delete f;
   return LB200_OK;
+}
+
+int lb200_fock_set_profile(lb200_fock* f, int on) {
+  if (!f) return LB200_ERR_INVALID;
+  f->profile = on != 0;
+  return LB200_OK;
+}
+
+long long lb200_fock_get_profile(const lb200_fock* f, double* rows, long long cap) {
+  if (!f) return LB200_ERR_INVALID;
+  const long long n = (long long)f->prof.size();
+  if (!rows) return n;
+  for (long long i = 0; i < n && i < cap; ++i) {
+    const auto& e = f->prof[i];
+    double* o = rows + 9 * i;
+    for (int k = 0; k < 6; ++k) o[k] = e.c[k];
+    o[6] = e.ms; o[7] = e.nq; o[8] = e.nprim;
+  }
+  return n;
 }
 
 int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks) {
@@ -449,7 +474,11 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   if (!rc && !f->d_D) rc = check_cuda(ctx, cudaMalloc(&f->d_D, n2 * 8), "cudaMalloc(D)");
   if (rc) return rc;
   const long long launches0 = ctx->launches;
-  cudaEvent_t ev0, ev1;
+  struct Events {   // destroyed on every exit path
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } evs;
+  cudaEvent_t &ev0 = evs.e[0], &ev1 = evs.e[1], &pe0 = evs.e[2], &pe1 = evs.e[3];
   cudaEventCreate(&ev0);
   cudaEventCreate(&ev1);
   cudaEventRecord(ev0, st);
@@ -484,10 +513,12 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   double nquartets = 0, ncand = 0;
   std::vector<unsigned> jmax;
   // LB200_FOCK_PROFILE=1: per class-pair device time (one sync per launch; diagnostics only)
-  const bool profile = stats && std::getenv("LB200_FOCK_PROFILE");
-  struct Prof { int c[6]; double ms, nq; };
-  std::vector<Prof> prof;
-  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  const bool env_profile = stats && std::getenv("LB200_FOCK_PROFILE");
+  const bool profile = env_profile || f->profile;
+  using Prof = lb200_fock::ProfRow;
+  std::vector<Prof>& prof = f->prof;
+  prof.clear();
+  if (profile && !f->d_primcount) cudaMalloc(&f->d_primcount, 8);
   if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const size_t ncls = f->classes.size();
   for (size_t X = 0; X < ncls && !rc; ++X)
@@ -567,7 +598,12 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.fock_precision = fock_precision;
           p.needed_engine_precision = needed_engine_precision;
           p.ln_needed_engine_precision = std::log(needed_engine_precision);
-          if (profile) cudaEventRecord(pe0, st);
+          p.prim_counter = nullptr;
+          if (profile) {
+            cudaMemsetAsync(f->d_primcount, 0, 8, st);
+            p.prim_counter = f->d_primcount;
+            cudaEventRecord(pe0, st);
+          }
           // LB200_FOCK_SCREEN_ONLY=1 (diagnostics): enumerate and screen, skip the class kernels
           static const bool screen_only = std::getenv("LB200_FOCK_SCREEN_ONLY") != nullptr;
           if (!screen_only)
@@ -580,14 +616,17 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
             float ms = 0;
             cudaEventElapsedTime(&ms, pe0, pe1);
             unsigned c = 0;
+            unsigned long long np = 0;
             cudaMemcpy(&c, f->d_count, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&np, f->d_primcount, 8, cudaMemcpyDeviceToHost);
             bool found = false;
             for (auto& e : prof)
               if (e.c[0] == B.la && e.c[1] == B.lb && e.c[2] == Kt.la && e.c[3] == Kt.lb &&
                   e.c[4] == B.bucket && e.c[5] == Kt.bucket) {
-                e.ms += ms; e.nq += c; found = true;
+                e.ms += ms; e.nq += c; e.nprim += (double)np; found = true;
               }
-            if (!found) prof.push_back(Prof{{B.la, B.lb, Kt.la, Kt.lb, B.bucket, Kt.bucket}, ms, (double)c});
+            if (!found)
+              prof.push_back(Prof{{B.la, B.lb, Kt.la, Kt.lb, B.bucket, Kt.bucket}, ms, (double)c, (double)np});
           }
           if (stats) {  // optional accounting costs a sync per chunk
             unsigned c = 0;
@@ -602,6 +641,8 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   if (rc) return rc;
   if (profile) {
     std::sort(prof.begin(), prof.end(), [](const Prof& a, const Prof& b) { return a.ms > b.ms; });
+  }
+  if (env_profile) {
     double tot = 0;
     for (auto& e : prof) tot += e.ms;
     std::fprintf(stderr, "lb200 fock profile: %zu class pairs, %.2f ms in class kernels\n", prof.size(), tot);
@@ -609,8 +650,6 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
       std::fprintf(stderr, "  (%d%d|%d%d) buckets %d,%d %10.3f ms %5.1f%% %12.0f quartets %8.2f ns/quartet\n",
                    e.c[0], e.c[1], e.c[2], e.c[3], e.c[4], e.c[5], e.ms, 100 * e.ms / tot, e.nq,
                    e.nq > 0 ? 1e6 * e.ms / e.nq : 0.0);
-    cudaEventDestroy(pe0);
-    cudaEventDestroy(pe1);
   }
   double* d_G = nullptr;
   if (G_on_device) {
@@ -625,8 +664,6 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock build");
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   if (stats) {
     stats[0] = nquartets;
     stats[1] = (double)(ctx->launches - launches0);

@@ -138,6 +138,7 @@ template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class_any(const EriParams& p, const RowInfo* rows, int mode, int num_sms,
                              cudaStream_t stream) {
   if (mode == kModeFock) return launch_class<LA, LB, LC, LD, kModeFock>(p, rows, num_sms, stream);
+  if (mode == kModePrereq) return launch_class<LA, LB, LC, LD, kModePrereq>(p, rows, num_sms, stream);
   return launch_class<LA, LB, LC, LD, kModeStoreCart>(p, rows, num_sms, stream);
 }
 

@@ -46,7 +46,18 @@ enum ScreeningMethod : int {  // values follow shell.h:1041-1059
   kScreenSchwarzInf = 0x1000
 };
 
-enum EriMode : int { kModeStoreCart = 0, kModeStore = 1, kModeFock = 2 };
+enum EriMode : int { kModeStoreCart = 0, kModeStore = 1, kModeFock = 2, kModePrereq = 3 };
+
+// kModePrereq: the caller supplies the per-primitive prerequisites itself -- the members of the
+// reference's Libint_t that Engine::compute2 fills (engine.impl.h:1514-1641): (ss|ss)^(m) =
+// F_m(T) * pfac, PA, QC, WP, WQ, oo2z, oo2e, oo2ze, roz, roe -- in the CALLER's bra/ket orientation;
+// the kernel picks the side it needs.  This is what libint2_build_eri[la][lb][lc][ld](Libint_t*)
+// receives (iface.cu).
+struct PrereqRec {
+  double F[kBoysTableMmax + 1];
+  double PA[3], QC[3], WP[3], WQ[3];
+  double oo2z, oo2e, oo2ze, roz, roe;
+};
 
 struct EriParams {
   PairBlock bra, ket;        // kernel-internal orientation: bra = "lane side"
@@ -60,6 +71,7 @@ struct EriParams {
   int swap_tasks;             // 1: tasks are (ket pair, bra pair) in kernel orientation
   int uncontracted;           // 1: no pair of either block holds more than one primitive pair
   unsigned* work_counter;    // dynamic scheduling counter (zeroed by host)
+  unsigned long long* prim_counter;  // profiling only (else null): surviving primitive quartets
   const double* boys;        // [kBoysNInt][kBoysTableMmax+1][8]
   // primitive screening (engine.impl.h:1313-1314,1371-1386)
   int screening;
@@ -78,6 +90,10 @@ struct EriParams {
   double fock_precision;
   double ln_needed_engine_precision;
   double needed_engine_precision;
+  // kModePrereq: records of task t are prereq[prereq_off[t] .. prereq_off[t+1]); geom[t] = AB[3], CD[3]
+  const PrereqRec* prereq;
+  const int* prereq_off;
+  const double* prereq_geom;
   // sparse cart->pure tables (context.cu) for the run-time purity path of the Fock digestion
   const int* sph_rowptr;     // [(kMaxShellL+1)][2*kMaxShellL+2]
   const int* sph_col;

@@ -82,6 +82,14 @@ extern "C" {
 
 int lbo_init() {
   if (!libint2::initialized()) libint2::initialize();
+  // libint2::initialized() lives in an inline (process-wide unique) singleton: when a second library
+  // built from this file on another kernel library is loaded into the same process, initialize() is
+  // skipped for it -- fill this library's own function tables explicitly (idempotent).
+  static bool tables_filled = false;
+  if (!tables_filled) {
+    libint2_static_init();
+    tables_filled = true;
+  }
   return 0;
 }
 
@@ -452,9 +460,14 @@ int lbo_fock_build(void* h, const double* D, double precision, int use_schwarz, 
 // independent engines (the reference's parallel model,
 // doc/wiki/using-modern-CPlusPlus-API.md:387-389). quartets index into the shell
 // table; returns wall seconds, checksum in *sum.
+// use_pairs != 0: the ShellPair of every distinct (bra1,bra2) / (ket1,ket2) is precomputed
+// outside the timed region and handed to compute2, as the reference's own direct-SCF driver
+// does (hartree-fock++.cc:1383-1431,1697); 0: compute2 rebuilds both pairs per quartet
+// (engine.impl.h:1259-1276).
 double lbo_time_quartets(int nshell, const int* l, const int* pure, const int* nprim,
                          const double* O, const double* alpha, const double* coeff,
-                         int coeff_is_raw, long nq, const int* q4, int nthreads, double* sum) {
+                         int coeff_is_raw, long nq, const int* q4, int nthreads, int use_pairs,
+                         double* sum) {
   lbo_init();
   auto sh = make_shells(nshell, l, pure, nprim, O, alpha, coeff, coeff_is_raw);
   int max_nprim = 0, max_l = 0;
@@ -467,6 +480,25 @@ double lbo_time_quartets(int nshell, const int* l, const int* pure, const int* n
   engines[0] = Engine(Operator::coulomb, max_nprim, max_l, 0);
   for (int i = 1; i < nthr; ++i) engines[i] = engines[0];
   std::vector<double> sums(nthr, 0.0);
+  std::unordered_map<long long, std::shared_ptr<ShellPair>> pairs;
+  std::vector<const ShellPair*> spb, spk;
+  if (use_pairs) {
+    const double ln_prec = std::log(engines[0].precision());
+    auto get = [&](int a, int b) {
+      const long long key = (long long)a * nshell + b;
+      auto it = pairs.find(key);
+      if (it == pairs.end())
+        it = pairs.emplace(key, std::make_shared<ShellPair>(sh[a], sh[b], ln_prec,
+                                                            ScreeningMethod::Original)).first;
+      return it->second.get();
+    };
+    spb.resize(nq);
+    spk.resize(nq);
+    for (long q = 0; q < nq; ++q) {
+      spb[q] = get(q4[4 * q], q4[4 * q + 1]);
+      spk[q] = get(q4[4 * q + 2], q4[4 * q + 3]);
+    }
+  }
   const auto t0 = std::chrono::high_resolution_clock::now();
   parallel_do(nthr, [&](int tid) {
     auto& e = engines[tid];
@@ -474,7 +506,9 @@ double lbo_time_quartets(int nshell, const int* l, const int* pure, const int* n
     double s = 0;
     for (long q = tid; q < nq; q += nthr) {
       e.compute2<Operator::coulomb, BraKet::xx_xx, 0>(sh[q4[4 * q]], sh[q4[4 * q + 1]],
-                                                      sh[q4[4 * q + 2]], sh[q4[4 * q + 3]]);
+                                                      sh[q4[4 * q + 2]], sh[q4[4 * q + 3]],
+                                                      use_pairs ? spb[q] : nullptr,
+                                                      use_pairs ? spk[q] : nullptr);
       if (buf[0]) s += buf[0][0];
     }
     sums[tid] = s;
@@ -484,6 +518,46 @@ double lbo_time_quartets(int nshell, const int* l, const int* pure, const int* n
   for (auto v : sums) s += v;
   if (sum) *sum = s;
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// A list of shell quartets of one class through the reference Engine (xx_xx), results
+// (row-major n1*n2*n3*n4, pure where flagged) written to out[q * blk ...]; a set the Engine
+// screens out entirely (results()[0] == nullptr) gives zeros.  Returns blk, < 0 on error.
+long lbo_compute_batch(int nshell, const int* l, const int* pure, const int* nprim,
+                       const double* O, const double* alpha, const double* coeff,
+                       int coeff_is_raw, long nq, const int* q4, int nthreads, double precision,
+                       double* out) {
+  lbo_init();
+  if (nq <= 0) return 0;
+  auto sh = make_shells(nshell, l, pure, nprim, O, alpha, coeff, coeff_is_raw);
+  int max_nprim = 0, max_l = 0;
+  for (auto& s : sh) {
+    max_nprim = std::max<int>(max_nprim, s.nprim());
+    max_l = std::max<int>(max_l, s.contr[0].l);
+  }
+  const long blk = (long)(sh[q4[0]].size() * sh[q4[1]].size() * sh[q4[2]].size() * sh[q4[3]].size());
+  const int nthr = std::max(1, nthreads);
+  try {
+    std::vector<Engine> engines(nthr);
+    engines[0] = Engine(Operator::coulomb, max_nprim, max_l, 0, precision);
+    for (int i = 1; i < nthr; ++i) engines[i] = engines[0];
+    parallel_do(nthr, [&](int tid) {
+      auto& e = engines[tid];
+      const auto& buf = e.results();
+      for (long q = tid; q < nq; q += nthr) {
+        e.compute2<Operator::coulomb, BraKet::xx_xx, 0>(sh[q4[4 * q]], sh[q4[4 * q + 1]],
+                                                        sh[q4[4 * q + 2]], sh[q4[4 * q + 3]]);
+        if (buf[0])
+          std::memcpy(out + q * blk, buf[0], blk * sizeof(double));
+        else
+          std::memset(out + q * blk, 0, blk * sizeof(double));
+      }
+    });
+  } catch (std::exception& e) {
+    std::fprintf(stderr, "lbo_compute_batch: %s\n", e.what());
+    return -1;
+  }
+  return blk;
 }
 
 // BasisSet(name, atoms) through the reference's own G94 reader (basis.h.in:473-617);

@@ -31,6 +31,7 @@
 
 #include <libint2/util/generated/libint2_iface.h>
 
+#include <algorithm>
 #include <cassert>
 #include <cstdlib>
 #include <cstring>
@@ -74,7 +75,7 @@ struct Scratch {
   // [e][f] -> block of ncart(e)*ncart(f)*(nm) doubles, element ((ie*nf+jf)*nm + m)
   std::vector<double> v;
   std::vector<double> contr;  // contracted (e0|f0), e in [la,la+lb], f in [lc,lc+ld]
-  std::vector<double> hrr1, hrr2;
+  std::vector<double> hrr1, hrr2, ket;  // HRR arenas, grown on demand, never freed
 };
 
 inline const double* fm_ptr(const Libint_t* p) {
@@ -216,29 +217,55 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
   }
 
   // ---------------- HRR, ket first: (e0|c d) from (e0|f0), hrr.h:324 -----------
-  // after this step K[e] holds (e0|lc ld) as [ie][ic][id]
+  // after this step K[e] holds (e0|lc ld) as [ie][ic][id].  All intermediates live in two
+  // thread-local arenas that are only ever grown (no allocation per call).
   const int nc = ncart(lc), nd = ncart(ld), na = ncart(la), nb = ncart(lb);
-  std::vector<std::vector<double>> K(emax + 1);
+  const int ncd = nc * nd;
+  size_t kreq = 0, koff[kMaxL + 1];
+  for (int e = la; e <= emax; ++e) { koff[e] = kreq; kreq += (size_t)ncart(e) * ncd; }
+  size_t levmax = 0;
+  for (int e = la; e <= emax; ++e) {
+    for (int dd = 0; dd <= ld; ++dd) {
+      size_t n = 0;
+      for (int c = lc; c <= fmax - dd; ++c) n += (size_t)ncart(e) * ncart(c) * ncart(dd);
+      levmax = std::max(levmax, n);
+    }
+  }
+  for (int bb = 0; bb <= lb; ++bb) {
+    size_t n = 0;
+    for (int a = la; a <= emax - bb; ++a) n += (size_t)ncart(a) * ncart(bb) * ncd;
+    levmax = std::max(levmax, n);
+  }
+  if (s.hrr1.size() < levmax) s.hrr1.resize(levmax);
+  if (s.hrr2.size() < levmax) s.hrr2.resize(levmax);
+  if (s.ket.size() < kreq) s.ket.resize(kreq);
   {
     double CD[3] = {0, 0, 0};
     if (ld > 0) { CD[0] = inteval[0].CD_x[0]; CD[1] = inteval[0].CD_y[0]; CD[2] = inteval[0].CD_z[0]; }
     for (int e = la; e <= emax; ++e) {
       const int ne = ncart(e);
-      // cur[c - lc] : (e0| c, dcur) stored [ie][ic][idcur]
-      std::vector<std::vector<double>> cur(fmax - lc + 1);
-      for (int c = lc; c <= fmax; ++c) {
-        cur[c - lc].assign(s.contr.begin() + coff[e][c],
-                           s.contr.begin() + coff[e][c] + ne * ncart(c));
+      // level dd: blocks c = lc .. fmax-dd, block c stored [ie][ic][id] at loff[c - lc]
+      double* cur = s.hrr1.data();
+      double* nxt = s.hrr2.data();
+      size_t curoff[kMaxL + 2], nxtoff[kMaxL + 2];
+      {
+        size_t o = 0;
+        for (int c = lc; c <= fmax; ++c) {
+          curoff[c - lc] = o;
+          std::memcpy(cur + o, s.contr.data() + coff[e][c], sizeof(double) * ne * ncart(c));
+          o += (size_t)ne * ncart(c);
+        }
       }
       for (int dd = 1; dd <= ld; ++dd) {
-        std::vector<std::vector<double>> nxt(fmax - dd - lc + 1);
         const int ndd = ncart(dd), ndm1 = ncart(dd - 1);
+        size_t o = 0;
         for (int c = lc; c <= fmax - dd; ++c) {
           const int ncc = ncart(c), ncp1 = ncart(c + 1);
-          auto& out = nxt[c - lc];
-          out.resize((size_t)ne * ncc * ndd);
-          const auto& lo = cur[c - lc];      // (e0| c,   dd-1)
-          const auto& hi = cur[c + 1 - lc];  // (e0| c+1, dd-1)
+          nxtoff[c - lc] = o;
+          double* out = nxt + o;
+          o += (size_t)ne * ncc * ndd;
+          const double* lo = cur + curoff[c - lc];      // (e0| c,   dd-1)
+          const double* hi = cur + curoff[c + 1 - lc];  // (e0| c+1, dd-1)
           for (int ie = 0; ie < ne; ++ie)
             for (int ic = 0; ic < ncc; ++ic) {
               const auto& qc = ct.xyz[c][ic];
@@ -257,30 +284,34 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
               }
             }
         }
-        cur.swap(nxt);
+        std::swap(cur, nxt);
+        for (int c = lc; c <= fmax - dd; ++c) curoff[c - lc] = nxtoff[c - lc];
       }
-      K[e] = std::move(cur[0]);
+      std::memcpy(s.ket.data() + koff[e], cur + curoff[0], sizeof(double) * ne * ncd);
     }
   }
 
   // ---------------- HRR, bra: (a b|cd) from (e0|cd), hrr.h:246 -----------------
-  const int ncd = nc * nd;
-  std::vector<double> result;
+  const double* result = nullptr;
   {
     double AB[3] = {0, 0, 0};
     if (lb > 0) { AB[0] = inteval[0].AB_x[0]; AB[1] = inteval[0].AB_y[0]; AB[2] = inteval[0].AB_z[0]; }
-    // cur[a - la] : (a, bcur|cd) stored [ia][ibcur][cd]
-    std::vector<std::vector<double>> cur(emax - la + 1);
-    for (int a = la; a <= emax; ++a) cur[a - la] = std::move(K[a]);
+    // level bb: blocks a = la .. emax-bb, block a stored [ia][ibcur][cd]
+    const double* cur = s.ket.data();
+    size_t curoff[kMaxL + 2], nxtoff[kMaxL + 2];
+    for (int a = la; a <= emax; ++a) curoff[a - la] = koff[a];
+    double* bufs[2] = {s.hrr1.data(), s.hrr2.data()};
     for (int bb = 1; bb <= lb; ++bb) {
-      std::vector<std::vector<double>> nxt(emax - bb - la + 1);
       const int nbb = ncart(bb), nbm1 = ncart(bb - 1);
+      double* nxt = bufs[bb & 1];
+      size_t o = 0;
       for (int a = la; a <= emax - bb; ++a) {
-        const int naa = ncart(a), nap1 = ncart(a + 1);
-        auto& out = nxt[a - la];
-        out.resize((size_t)naa * nbb * ncd);
-        const auto& lo = cur[a - la];
-        const auto& hi = cur[a + 1 - la];
+        const int naa = ncart(a);
+        nxtoff[a - la] = o;
+        double* out = nxt + o;
+        o += (size_t)naa * nbb * ncd;
+        const double* lo = cur + curoff[a - la];
+        const double* hi = cur + curoff[a + 1 - la];
         for (int ia = 0; ia < naa; ++ia) {
           const auto& qa = ct.xyz[a][ia];
           for (int ib = 0; ib < nbb; ++ib) {
@@ -292,20 +323,20 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
             ++ap1[dir];
             const int ibm1 = cart_index(bb - 1, bm1[0], bm1[1]);
             const int iap1 = cart_index(a + 1, ap1[0], ap1[1]);
-            const double* h = hi.data() + ((size_t)iap1 * nbm1 + ibm1) * ncd;
-            const double* l = lo.data() + ((size_t)ia * nbm1 + ibm1) * ncd;
-            double* o = out.data() + ((size_t)ia * nbb + ib) * ncd;
-            for (int k = 0; k < ncd; ++k) o[k] = h[k] + AB[dir] * l[k];
+            const double* h = hi + ((size_t)iap1 * nbm1 + ibm1) * ncd;
+            const double* l = lo + ((size_t)ia * nbm1 + ibm1) * ncd;
+            double* ov = out + ((size_t)ia * nbb + ib) * ncd;
+            for (int k = 0; k < ncd; ++k) ov[k] = h[k] + AB[dir] * l[k];
           }
         }
       }
-      cur.swap(nxt);
+      cur = nxt;
+      for (int a = la; a <= emax - bb; ++a) curoff[a - la] = nxtoff[a - la];
     }
-    result = std::move(cur[0]);
+    result = cur + curoff[0];
   }
 
-  assert((int)result.size() == na * nb * ncd);
-  std::memcpy(inteval[0].stack, result.data(), sizeof(double) * result.size());
+  std::memcpy(inteval[0].stack, result, sizeof(double) * na * nb * ncd);
   inteval[0].targets[0] = inteval[0].stack;
 }
 

