@@ -272,6 +272,7 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     d.pure_a = bs1->pure[s1[0]]; d.pure_b = bs2->pure[s2[0]];
   } else {
     d.la = d.lb = d.pure_a = d.pure_b = 0;
+    d.unit_b = 0;
   }
   P->prim_off.assign(npair + 1, 0);
   P->shell.resize(2 * (size_t)npair);
@@ -300,6 +301,11 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     const int np1 = bs1->nprim[a], np2 = bs2->nprim[b];
     const int l1 = bs1->l[a], l2 = bs2->l[b];
     const bool unit_b = bs2->is_unit(b);
+    if (i == 0) d.unit_b = unit_b ? 1 : 0;
+    if ((d.unit_b != 0) != unit_b) {
+      delete P;
+      return set_error(ctx, LB200_ERR_INVALID, "unit and ordinary second shells cannot share a block");
+    }
     for (int p1 = 0; p1 < np1; ++p1)
       for (int p2 = 0; p2 < np2; ++p2) {
         const double a1 = bs1->alpha[bs1->off[a] + p1], a2 = bs2->alpha[bs2->off[b] + p2];
@@ -345,15 +351,14 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
         }
         PrimPair pp{};
         pp.P[0] = Pc[0]; pp.P[1] = Pc[1]; pp.P[2] = Pc[2];
-        for (int k = 0; k < 3; ++k) pp.PA[k] = unit_b ? 0.0 : Pc[k] - A[k];
         const double K = 5.9149671727956128778 * std::exp(minus_rho_times_AB2) * oogamma;
         pp.Kc = K * (bs1->coeff[bs1->off[a] + p1] * bs2->coeff[bs2->off[b] + p2]);
         pp.gamma = gamma;
         pp.oog = oogamma;
         pp.ln_scr = ln_screen_fac;
         pp.nonsph = nonsph;
-        pp.pad_ = K;  // unscaled K kept for lb200_pairs_get
         P->prim.push_back(pp);
+        P->Kraw.push_back(K);  // unscaled K kept for lb200_pairs_get
         P->p1p2.push_back(p1);
         P->p1p2.push_back(p2);
       }
@@ -361,12 +366,22 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     P->prim_off[i + 1] = (int)P->prim.size();
     d.max_nprim = std::max(d.max_nprim, P->prim_off[i + 1] - P->prim_off[i]);
   }
-  // one device allocation: prim | AB | schwarz | prim_off | shell | bf | gidx
+  // one device allocation: prim | geom | schwarz | prim_off | shell | gidx
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t n = (size_t)npair;
-  const size_t o_prim = 0, o_AB = al(o_prim + P->prim.size() * sizeof(PrimPair));
-  const size_t o_sw = al(o_AB + 3 * n * 8), o_po = al(o_sw + n * 8), o_sh = al(o_po + (n + 1) * 4);
-  const size_t o_bf = al(o_sh + 2 * n * 4), o_gi = al(o_bf + 2 * n * 4), total = al(o_gi + n * 4) + 256;
+  const size_t o_prim = 0, o_geom = al(o_prim + P->prim.size() * sizeof(PrimPair));
+  const size_t o_sw = al(o_geom + n * sizeof(PairGeom)), o_po = al(o_sw + n * 8), o_sh = al(o_po + (n + 1) * 4);
+  const size_t o_gi = al(o_sh + 2 * n * 4), total = al(o_gi + n * 4) + 256;
+  std::vector<PairGeom> geom(n);
+  for (size_t i = 0; i < n; ++i) {
+    PairGeom& g = geom[i];
+    for (int k = 0; k < 3; ++k) {
+      g.A[k] = bs1->O[3 * (size_t)P->shell[2 * i] + k];
+      g.AB[k] = P->AB[3 * i + k];
+    }
+    g.bf[0] = P->bf[2 * i]; g.bf[1] = P->bf[2 * i + 1];
+    g.shell[0] = P->shell[2 * i]; g.shell[1] = P->shell[2 * i + 1];
+  }
   cudaSetDevice(ctx->device);
   int rc = check_cuda(ctx, cudaMalloc(&P->d_block, total), "cudaMalloc(pairs)");
   if (rc) { delete P; return rc; }
@@ -375,25 +390,23 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
   for (size_t i = 0; i < n; ++i) {
     const long long hi = std::max(P->shell[2 * i], P->shell[2 * i + 1]);
     const long long lo = std::min(P->shell[2 * i], P->shell[2 * i + 1]);
-    gidx[i] = (int)(hi * (hi + 1) / 2 + lo);
+    gidx[i] = (int)(hi * (hi + 1) / 2 + lo);   // < 2^31 for < 65536 shells (checked by lb200_fock_create)
   }
   std::vector<double> sw(n, 0.0);
   if (pair_schwarz) sw.assign(pair_schwarz, pair_schwarz + n);
   cudaMemcpy(base + o_prim, P->prim.data(), P->prim.size() * sizeof(PrimPair), cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_AB, P->AB.data(), 3 * n * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_geom, geom.data(), n * sizeof(PairGeom), cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_sw, sw.data(), n * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_po, P->prim_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_sh, P->shell.data(), 2 * n * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_bf, P->bf.data(), 2 * n * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_gi, gidx.data(), n * 4, cudaMemcpyHostToDevice);
   rc = check_cuda(ctx, cudaGetLastError(), "upload pairs");
   if (rc) { cudaFree(P->d_block); delete P; return rc; }
   d.prim = reinterpret_cast<const PrimPair*>(base + o_prim);
-  d.AB = reinterpret_cast<const double*>(base + o_AB);
+  d.geom = reinterpret_cast<const PairGeom*>(base + o_geom);
   d.schwarz = reinterpret_cast<const double*>(base + o_sw);
   d.prim_off = reinterpret_cast<const int*>(base + o_po);
   d.shell = reinterpret_cast<const int*>(base + o_sh);
-  d.bf = reinterpret_cast<const int*>(base + o_bf);
   d.gidx = reinterpret_cast<const int*>(base + o_gi);
   *out = P;
   return LB200_OK;
@@ -428,6 +441,8 @@ int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket
   BatchPlan pl;
   int rc = plan_batch(ctx, bra, ket, pl);
   if (rc) return rc;
+  if (ntasks < 0 || ntasks > 0xffffffffll)
+    return set_error(ctx, LB200_ERR_INVALID, "more than 2^32 - 1 tasks in one launch");
   EriParams p{};
   p.bra = pl.swap ? ket->dev : bra->dev;
   p.ket = pl.swap ? bra->dev : ket->dev;
@@ -489,7 +504,7 @@ int lb200_pairs_get(const lb200_pairs* p, int i, double* out, int cap) {
     const PrimPair& pp = p->prim[k];
     double* o = out + 9 * (k - b);
     o[0] = pp.P[0]; o[1] = pp.P[1]; o[2] = pp.P[2];
-    o[3] = pp.pad_; o[4] = pp.oog; o[5] = pp.nonsph; o[6] = pp.ln_scr;
+    o[3] = p->Kraw[k]; o[4] = pp.oog; o[5] = pp.nonsph; o[6] = pp.ln_scr;
     o[7] = p->p1p2[2 * k]; o[8] = p->p1p2[2 * k + 1];
   }
   return e - b;

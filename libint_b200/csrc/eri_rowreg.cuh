@@ -61,7 +61,8 @@ struct RR {
   // Fock mode: final integrals [NAB][CS] at HDR, then a second buffer used first as the
   // row->column transpose buffer and afterwards by the cart->pure passes
   static constexpr int OFF_B2 = HDR + NAB * CS;
-  static constexpr int FOCK_DOUBLES = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);
+  static constexpr int OFF_D = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);  // staged density blocks
+  static constexpr int FOCK_DOUBLES = OFF_D + fock_dblock_doubles<LA, LB, LC, LD>();
   static constexpr int STORE_DOUBLES = OFF_B2 + (LB > 0 ? NCD * RTP : 0);
   // Stride between the regions of consecutive quartets.  The lanes of a warp that belong to
   // different quartets touch the same offset of their regions at the same time, so the stride
@@ -235,6 +236,14 @@ __device__ __forceinline__ void rr_hrr_regs(const double (&in0)[N0], const doubl
   }
 }
 
+// profiling only: one atomic per warp into one of 64 counters (a single hot address would serialise
+// billions of atomics and distort the very timings being profiled); every lane of the warp calls it
+__device__ __forceinline__ void count_primitives(unsigned long long* counters, int n) {
+  const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)n);
+  if ((threadIdx.x & 31) == 0 && tot)
+    atomicAdd(counters + ((blockIdx.x + (threadIdx.x >> 5)) & (kPrimCounters - 1)), (unsigned long long)tot);
+}
+
 __device__ __forceinline__ double sel3(int d, double x, double y, double z) {
   return d == 0 ? x : (d == 1 ? y : z);
 }
@@ -357,15 +366,22 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       if (valid && rmeta.row == 0 && nit > 0) atomicMax(&s_maxit[round % 3], nit);
     }
 
-    double CD[3] = {0, 0, 0};
+    double CD[3] = {0, 0, 0}, Ac[3] = {0, 0, 0}, Cc[3] = {0, 0, 0};   // C - D, centres A and C
     if (valid) {
       if constexpr (PREREQ) {   // swap_tasks: this kernel's ket is the caller's bra
         const double* gv = p.prereq_geom + 6 * (size_t)task + (p.swap_tasks ? 0 : 3);
         CD[0] = gv[0]; CD[1] = gv[1]; CD[2] = gv[2];
       } else {
-        CD[0] = p.ket.AB[3 * ik]; CD[1] = p.ket.AB[3 * ik + 1]; CD[2] = p.ket.AB[3 * ik + 2];
+        const PairGeom& gk = p.ket.geom[ik];
+        CD[0] = gk.AB[0]; CD[1] = gk.AB[1]; CD[2] = gk.AB[2];
+        Cc[0] = gk.A[0]; Cc[1] = gk.A[1]; Cc[2] = gk.A[2];
+        if constexpr (EMAX > 0) {
+          const PairGeom& gb = p.bra.geom[ib];
+          Ac[0] = gb.A[0]; Ac[1] = gb.A[1]; Ac[2] = gb.A[2];
+        }
       }
     }
+    const bool bra_unit = p.bra.unit_b != 0, ket_unit = p.ket.unit_b != 0;
     const double npbraket = (double)nb * (double)nk;
     double acc[K::NFT];
     static_for<K::NFT>([&](auto ic) { acc[decltype(ic)::value] = 0.0; });
@@ -439,8 +455,8 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           const double W = gp * bp.P[d] + gq * kp.P[d];
           WP[d] = W - bp.P[d];
           WQ[d] = W - kp.P[d];
-          PA[d] = bp.PA[d];
-          QC[d] = kp.PA[d];
+          PA[d] = bra_unit ? 0.0 : bp.P[d] - Ac[d];   // engine.impl.h:1514-1537
+          QC[d] = ket_unit ? 0.0 : kp.P[d] - Cc[d];
         }
         oo2z = 0.5 * bp.oog;
         roz = rho * bp.oog;
@@ -465,14 +481,34 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           F[m] = on ? p.prereq[pb0 + it].F[m] : 0.0;
         });
       } else if constexpr (NEC == 1) {
-        static_for<L + 1>([&](auto mc) {
-          constexpr int m = decltype(mc)::value;
-          F[m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
-        });
+        if constexpr (FOCK && LB200_BOYS_RECUR) {
+          if (on) {
+            boys_all<L>(p.boys, Targ, F);
+            static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] *= pfac; });
+          } else {
+            static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] = 0.0; });
+          }
+        } else {
+          static_for<L + 1>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            F[m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
+          });
+        }
       } else {
-        if (lane_on)
+        if constexpr (FOCK && LB200_BOYS_RECUR) {
+          // one lane per quartet evaluates every order from one table row (boys_all)
+          if (lane_on && rmeta.row == 0) {
+            double Fa[L + 1];
+            if (on) boys_all<L>(p.boys, Targ, Fa);
+            static_for<L + 1>([&](auto mc) {
+              constexpr int m = decltype(mc)::value;
+              Q[K::OFF_F + m] = on ? Fa[m] * pfac : 0.0;
+            });
+          }
+        } else if (lane_on) {
           for (int m = rmeta.row; m <= L; m += NEC)
             Q[K::OFF_F + m] = on ? boys_value(p.boys, Targ, m) * pfac : 0.0;
+        }
         sync();
         static_for<L + 1>([&](auto mc) { F[decltype(mc)::value] = Q[K::OFF_F + decltype(mc)::value]; });
       }
@@ -552,8 +588,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     rr_hrr_regs<LC, LD>(acc, CD, H);
     const bool screened_out = (nsurv == 0);
     if constexpr (FOCK) {   // K_eff of the flop model, counted only when profiling
-      if (p.prim_counter && valid && rmeta.row == 0 && nsurv)
-        atomicAdd(p.prim_counter, (unsigned long long)nsurv);
+      if (p.prim_counter) count_primitives(p.prim_counter, (valid && rmeta.row == 0) ? nsurv : 0);
     }
     if (screened_out) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
 
@@ -567,7 +602,8 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
             const double* gv = p.prereq_geom + 6 * (size_t)task + (p.swap_tasks ? 3 : 0);
             Q[0] = gv[0]; Q[1] = gv[1]; Q[2] = gv[2];
           } else {
-            Q[0] = p.bra.AB[3 * ib]; Q[1] = p.bra.AB[3 * ib + 1]; Q[2] = p.bra.AB[3 * ib + 2];
+            const PairGeom& gb = p.bra.geom[ib];
+            Q[0] = gb.AB[0]; Q[1] = gb.AB[1]; Q[2] = gb.AB[2];
           }
         }
       }
@@ -633,7 +669,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       } else {
         // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet --------
         fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
-                                         Q + K::OFF_B2, ib, ik, deg);
+                                         Q + K::OFF_B2, Q + K::OFF_D, ib, ik, deg);
       }
     }
   }

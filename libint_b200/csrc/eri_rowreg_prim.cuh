@@ -58,8 +58,10 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int QPG = GROUP / B::NEC;
   static constexpr int NG = THREADS / GROUP;
   static constexpr int QPC = NG * QPG;
-  // pipeline stage (doubles): bra record 12 | ket record 12 | A-B 3 | C-D 3 | prep 4 | F_m
-  static constexpr int S_BP = 0, S_KP = 12, S_AB = 24, S_CD = 27, S_PREP = 30, S_F = 34;
+  // pipeline stage (doubles): bra record 8 | ket record 8 | bra PairGeom 8 (A, A-B, ints) |
+  // ket PairGeom 8 (C, C-D, ints) | prep 4 | F_m
+  static constexpr int S_BP = 0, S_KP = 8, S_GB = 16, S_GK = 24, S_AB = S_GB + 3, S_CD = S_GK + 3,
+                       S_PREP = 32, S_F = 36;
   static constexpr int PSTAGE = (S_F + B::L + 1 + 1) & ~1;
   static constexpr int PIPE = 2 * PSTAGE;
   // phase areas behind the pipeline stages
@@ -68,8 +70,8 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
   static constexpr bool HAS_FIN = TR || LB == 0 || FOCK;
   static constexpr int OFF_B2 = OFF_FIN + (HAS_FIN ? B::NAB * B::CS : 0);  // row -> column transpose buffer
-  static constexpr int P2_DOUBLES =
-      OFF_B2 + cmax(FOCK ? B::NAB * B::NCD : 0, LB > 0 ? B::NCD * B::RTP : 0);
+  static constexpr int OFF_D = OFF_B2 + cmax(FOCK ? B::NAB * B::NCD : 0, LB > 0 ? B::NCD * B::RTP : 0);
+  static constexpr int P2_DOUBLES = OFF_D + (FOCK ? fock_dblock_doubles<LA, LB, LC, LD>() : 0);
   static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
 #define LB200_PRIM_MINB_HI 4
@@ -135,8 +137,11 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     });
   }
   double* const Q = smem + (size_t)(lane_on ? q : g * QPG) * QSIZE;
-  const bool boys_lane = lane_on && rmeta.row <= L;
+  // Fock mode: one lane per quartet evaluates every order from one table row (boys_all)
+  constexpr bool RECUR = FOCK && LB200_BOYS_RECUR;
+  const bool boys_lane = lane_on && (RECUR ? rmeta.row == 0 : rmeta.row <= L);
 
+  const bool bra_unit = p.bra.unit_b != 0, ket_unit = p.ket.unit_b != 0;
   const unsigned ntasks = p.ntasks_dev ? *p.ntasks_dev : p.ntasks;
   const unsigned stride = gridDim.x * NG * QPG;
   unsigned base = (blockIdx.x * NG + g) * QPG;
@@ -175,22 +180,23 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     if (pb1 > pb0 && pk1 > pk0) { o.pb = pb0; o.pk = pk0; }
     return o;
   };
-  // 18 chunks per quartet: 6 + 6 sixteen-byte pieces of the two records, 3 + 3 doubles of A-B, C-D
-  // (A-B / C-D for every real task: the HRR of an all-screened quartet must see finite numbers)
+  // 16 sixteen-byte chunks per quartet: 4 + 4 pieces of the two records, 4 + 4 of the two PairGeoms
+  // (geometry for every real task: the HRR of an all-screened quartet must see finite numbers)
   auto issue_records = [&](const Off& o, double* S) {
     if (lane_on && o.ib >= 0) {
       const char* gb = reinterpret_cast<const char*>(p.bra.prim + (o.pb < 0 ? 0 : o.pb));
       const char* gk = reinterpret_cast<const char*>(p.ket.prim + (o.pk < 0 ? 0 : o.pk));
-      for (int c = rmeta.row; c < 18; c += NEC) {
-        if (c < 12) {
+      const char* hb = reinterpret_cast<const char*>(p.bra.geom + o.ib);
+      const char* hk = reinterpret_cast<const char*>(p.ket.geom + o.ik);
+      for (int c = rmeta.row; c < 16; c += NEC) {
+        if (c < 8) {
           if (o.pb < 0) continue;
-          if (c < 6) cp_async16(S + K::S_BP + 2 * c, gb + 16 * c);
-          else cp_async16(S + K::S_KP + 2 * (c - 6), gk + 16 * (c - 6));
-        } else if (c < 15) {
-          if constexpr (LB > 0)   // A - B is only needed by the bra HRR
-            cp_async8(S + K::S_AB + (c - 12), p.bra.AB + 3 * o.ib + (c - 12));
+          if (c < 4) cp_async16(S + K::S_BP + 2 * c, gb + 16 * c);
+          else cp_async16(S + K::S_KP + 2 * (c - 4), gk + 16 * (c - 4));
+        } else if (c < 12) {
+          cp_async16(S + K::S_GB + 2 * (c - 8), hb + 16 * (c - 8));
         } else {
-          cp_async8(S + K::S_CD + (c - 15), p.ket.AB + 3 * o.ik + (c - 15));
+          cp_async16(S + K::S_GK + 2 * (c - 12), hk + 16 * (c - 12));
         }
       }
     }
@@ -203,7 +209,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     bool on = o.pb >= 0;
     double oogpq = 0.0, rho = 0.0;
     if (on) {
-      const double lnb = S[K::S_BP + 9], lnk = S[K::S_KP + 9];
+      const double lnb = S[K::S_BP + 6], lnk = S[K::S_KP + 6];
       const double ln_prec = FOCK ? lnp : p.ln_precision;   // hartree-fock++.cc:1693-1695
       on = lnb + lnk > ln_prec;   // engine.impl.h:1313-1314
     }
@@ -211,14 +217,14 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       const double PQx = S[K::S_BP + 0] - S[K::S_KP + 0], PQy = S[K::S_BP + 1] - S[K::S_KP + 1],
                    PQz = S[K::S_BP + 2] - S[K::S_KP + 2];
       const double PQ2 = PQx * PQx + PQy * PQy + PQz * PQz;
-      const double gb = S[K::S_BP + 7], gk = S[K::S_KP + 7];
+      const double gb = S[K::S_BP + 4], gk = S[K::S_KP + 4];
       const double gpq = gb + gk;
       oogpq = 1.0 / gpq;
-      b.pfac = S[K::S_BP + 6] * S[K::S_KP + 6] * sqrt(gpq) * oogpq;
+      b.pfac = S[K::S_BP + 3] * S[K::S_KP + 3] * sqrt(gpq) * oogpq;
       if (p.screening & (kScreenOriginal | kScreenConservative)) {  // engine.impl.h:1371-1386
         double est = fabs(b.pfac);
         if (p.screening == kScreenConservative)
-          est *= fmax(1.0, S[K::S_BP + 10] * S[K::S_KP + 10]);  // npbra * npket = 1
+          est *= fmax(1.0, S[K::S_BP + 7] * S[K::S_KP + 7]);  // npbra * npket = 1
         if (est < p.precision) on = false;
       }
       rho = gb * gk * oogpq;
@@ -237,13 +243,24 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     if (!boys_lane || !b.on || b.T > kBoysTmax) return 0.0;
     int iv = (int)(b.T * 7.0);
     iv = iv > kBoysNInt - 1 ? kBoysNInt - 1 : iv;
-    const double* d = p.boys + ((size_t)iv * (kBoysTableMmax + 1) + rmeta.row) * 8;
+    const double* d = p.boys + ((size_t)iv * (kBoysTableMmax + 1) + (RECUR ? L : rmeta.row)) * 8;
     return __ldg(d) + __ldg(d + 4);
   };
   auto boys_finish = [&](const BoysState& b, double* S) {
-    if (boys_lane)
-      for (int m = rmeta.row; m <= L; m += NEC)
-        S[K::S_F + m] = b.on ? boys_value(p.boys, b.T, m) * b.pfac : 0.0;
+    if constexpr (RECUR) {
+      if (boys_lane) {
+        double Fa[L + 1];
+        if (b.on) boys_all<L>(p.boys, b.T, Fa);
+        static_for<L + 1>([&](auto mc) {
+          constexpr int m = decltype(mc)::value;
+          S[K::S_F + m] = b.on ? Fa[m] * b.pfac : 0.0;
+        });
+      }
+    } else {
+      if (boys_lane)
+        for (int m = rmeta.row; m <= L; m += NEC)
+          S[K::S_F + m] = b.on ? boys_value(p.boys, b.T, m) * b.pfac : 0.0;
+    }
   };
 
   // ---- prologue: round 0 of this group, unpipelined ---------------------------------------
@@ -277,8 +294,8 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     double PA[3], WP[3], QC[3], WQ[3], oo2z, roz, koo2e[6], roe, ce[3];
     {
       const double oogpq = S[K::S_PREP + 0], rho = S[K::S_PREP + 1];
-      const double gb = S[K::S_BP + 7], gk = S[K::S_KP + 7];
-      const double oogb = S[K::S_BP + 8], oogk = S[K::S_KP + 8];
+      const double gb = S[K::S_BP + 4], gk = S[K::S_KP + 4];
+      const double oogb = S[K::S_BP + 5], oogk = S[K::S_KP + 5];
       const double gp = oogpq * gb, gq = oogpq * gk;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -286,8 +303,8 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         const double W = gp * Pb + gq * Pk;
         WP[d] = W - Pb;
         WQ[d] = W - Pk;
-        PA[d] = S[K::S_BP + 3 + d];
-        QC[d] = S[K::S_KP + 3 + d];
+        PA[d] = bra_unit ? 0.0 : Pb - S[K::S_GB + d];   // engine.impl.h:1514-1537
+        QC[d] = ket_unit ? 0.0 : Pk - S[K::S_GK + d];
       }
       oo2z = 0.5 * oogb;
       roz = rho * oogb;
@@ -377,7 +394,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
     if constexpr (FOCK) {
-      if (p.prim_counter && valid && rmeta.row == 0 && on) atomicAdd(p.prim_counter, 1ull);
+      if (p.prim_counter) count_primitives(p.prim_counter, (valid && rmeta.row == 0 && on) ? 1 : 0);
     }
     sync();   // last cross-term reads done: the phase-2 areas alias the cross-term area
     constexpr int TBOFF = K::OFF_B2;
@@ -426,7 +443,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     if constexpr (FOCK) {
       // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet ------------
       fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && on, rmeta.row, Q + K::OFF_FIN, K::CS,
-                                           Q + K::OFF_B2, ocur.ib, ocur.ik, deg_cur);
+                                           Q + K::OFF_B2, Q + K::OFF_D, ocur.ib, ocur.ik, deg_cur);
     } else {
       // ---- coalesced copy-out (see eri_rowreg.cuh) ----------------------------------------
       constexpr int BLK = K::NAB * K::NCD;

@@ -49,8 +49,7 @@ struct lb200_fock {
   int* d_shellsize = nullptr;
   int4* d_tasks = nullptr;   // task records (types.cuh: EriParams::ftasks)
   unsigned* d_count = nullptr;
-  unsigned* d_jmax = nullptr;
-  long long task_cap = 0, jmax_cap = 0;
+  long long task_cap = 0;
   // per (bra class, ket class) timings of the last build, filled when profiling is on
   bool profile = false;
   unsigned long long* d_primcount = nullptr;
@@ -185,7 +184,8 @@ struct ScreenParams {
   PairBlock bra, ket;
   int same_class;
   int row0, nrow;            // bra rows of this chunk
-  const unsigned* jmax;      // per bra row (relative to row0): number of ket candidates
+  int nket;                  // pairs in the ket block
+  double thr_num;            // fock_precision / Dmax * (1 - 1e-12): candidate-prefix threshold numerator
   const double* bra_dn;      // [npair] Dnorm of the pair's own block (D12 / D34)
   const double* ket_dn;
   int stage_rows;            // 1: the two Dnorm rows of the bra shells fit in shared memory
@@ -217,13 +217,34 @@ __global__ void screen_kernel(const ScreenParams p) {
   extern __shared__ double s_rows[];   // [2][nshell] when p.stage_rows
   const int lane = threadIdx.x & 31;
   const int ns = p.nshell;
+  __shared__ unsigned s_jm;
   for (int r = blockIdx.x; r < p.nrow; r += gridDim.x) {
     const int i = p.row0 + r;
-    const unsigned jm = p.jmax[r];
-    if (jm == 0) continue;
-    const int s1 = p.bra.shell[2 * i], s2 = p.bra.shell[2 * i + 1];
     const double Ki = p.bra.schwarz[i];
     const int gi = p.bra.gidx[i];
+    // candidate prefix of this row: the kets are sorted by Schwarz bound (descending), and
+    // K_i * K_j * Dmax >= precision is necessary for survival -- a binary search instead of a
+    // host-made table (the host evaluates the same expression for its capacity planning);
+    // rows of other ranks have no candidates
+    if (threadIdx.x == 0) {
+      unsigned jm0 = (unsigned)p.nket;
+      if (p.use_schwarz) {
+        const double thr = p.thr_num / Ki;
+        int lo = 0, hi = p.nket;   // first j with schwarz[j] < thr
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (p.ket.schwarz[mid] < thr) hi = mid; else lo = mid + 1;
+        }
+        jm0 = (unsigned)lo;
+      }
+      if (p.nranks > 1 && task_owner(gi, 0, p.nranks) != p.rank) jm0 = 0;
+      s_jm = jm0;
+    }
+    __syncthreads();
+    const unsigned jm = s_jm;
+    __syncthreads();   // s_jm is rewritten by the next row
+    if (jm == 0) continue;
+    const int s1 = p.bra.shell[2 * i], s2 = p.bra.shell[2 * i + 1];
     const double D12 = p.bra_dn[i];
     const double* r1 = p.Dnorm + (size_t)s1 * ns;
     const double* r2 = p.Dnorm + (size_t)s2 * ns;
@@ -324,6 +345,9 @@ extern "C" {
 int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npair, const int* s1,
                       const int* s2, lb200_fock** out) {
   if (!ctx || !obs || !out || npair < 0) return LB200_ERR_INVALID;
+  // canonical pair indices s1(s1+1)/2+s2 are kept in 32 bits (PairBlock::gidx, task ownership)
+  if (obs->nshell >= 65536)
+    return set_error(ctx, LB200_ERR_INVALID, "Fock builder supports fewer than 65536 shells");
   cudaSetDevice(ctx->device);
   auto* f = new lb200_fock;
   f->ctx = ctx;
@@ -424,7 +448,6 @@ int lb200_fock_destroy(lb200_fock* f) {
   for (auto& c : f->classes) { lb200_pairs_destroy(c.pairs); cudaFree(c.d_dn); }
   cudaFree(f->d_D); cudaFree(f->d_F); cudaFree(f->d_Dnorm); cudaFree(f->d_scalar);
   cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize); cudaFree(f->d_tasks); cudaFree(f->d_count);
-  cudaFree(f->d_jmax);
   cudaFree(f->d_primcount);
   delete f;
   return LB200_OK;
@@ -510,6 +533,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
       return rc;
     f->task_cap = cap;
   }
+  const double thr_num = fock_precision / Dmax * (1.0 - 1e-12);
   double nquartets = 0, ncand = 0;
   std::vector<unsigned> jmax;
   // LB200_FOCK_PROFILE=1: per class-pair device time (one sync per launch; diagnostics only)
@@ -518,7 +542,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   using Prof = lb200_fock::ProfRow;
   std::vector<Prof>& prof = f->prof;
   prof.clear();
-  if (profile && !f->d_primcount) cudaMalloc(&f->d_primcount, 8);
+  if (profile && !f->d_primcount) cudaMalloc(&f->d_primcount, 8 * kPrimCounters);
   if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const size_t ncls = f->classes.size();
   for (size_t X = 0; X < ncls && !rc; ++X)
@@ -538,7 +562,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
         // host loop must stay ahead of eight GPUs' worth of class kernels)
         int lo = nk;   // first j with schwarz[j] < thr
         for (int i = 0; i < nb; ++i) {
-          const double thr = fock_precision / (Dmax * B.schwarz[i]) * (1.0 - 1e-12);
+          const double thr = thr_num / B.schwarz[i];   // same expression as screen_kernel
           while (lo > 0 && Kt.schwarz[lo - 1] < thr) --lo;
           jmax[i] = (unsigned)lo;
         }
@@ -550,12 +574,6 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           if (task_owner((int)(hi * (hi + 1) / 2 + lo), 0, nranks) != rank) jmax[i] = 0;
         }
       }
-      if ((long long)nb > f->jmax_cap) {
-        cudaFree(f->d_jmax);
-        if ((rc = check_cuda(ctx, cudaMalloc(&f->d_jmax, (size_t)nb * 4), "cudaMalloc(jmax)"))) break;
-        f->jmax_cap = nb;
-      }
-      cudaMemcpyAsync(f->d_jmax, jmax.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st);
       int row = 0;
       while (row < nb && !rc) {
         long long sum = 0;
@@ -568,7 +586,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           sp.bra = B.pairs->dev; sp.ket = Kt.pairs->dev;
           sp.same_class = (X == Y);
           sp.row0 = row; sp.nrow = r1 - row;
-          sp.jmax = f->d_jmax + row;
+          sp.nket = nk; sp.thr_num = thr_num;
           sp.Dnorm = f->d_Dnorm; sp.nshell = ns;
           sp.bra_dn = B.d_dn; sp.ket_dn = Kt.d_dn;
           sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
@@ -600,7 +618,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           p.ln_needed_engine_precision = std::log(needed_engine_precision);
           p.prim_counter = nullptr;
           if (profile) {
-            cudaMemsetAsync(f->d_primcount, 0, 8, st);
+            cudaMemsetAsync(f->d_primcount, 0, 8 * kPrimCounters, st);
             p.prim_counter = f->d_primcount;
             cudaEventRecord(pe0, st);
           }
@@ -616,9 +634,10 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
             float ms = 0;
             cudaEventElapsedTime(&ms, pe0, pe1);
             unsigned c = 0;
-            unsigned long long np = 0;
+            unsigned long long np = 0, npc[kPrimCounters];
             cudaMemcpy(&c, f->d_count, 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(&np, f->d_primcount, 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(npc, f->d_primcount, 8 * kPrimCounters, cudaMemcpyDeviceToHost);
+            for (int k = 0; k < kPrimCounters; ++k) np += npc[k];
             bool found = false;
             for (auto& e : prof)
               if (e.c[0] == B.la && e.c[1] == B.lb && e.c[2] == Kt.la && e.c[3] == Kt.lb &&

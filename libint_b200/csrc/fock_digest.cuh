@@ -11,6 +11,13 @@
 
 namespace lb200 {
 
+// doubles of shared memory fock_digest needs for the staged density blocks (Cartesian upper bound)
+template <int LA, int LB, int LC, int LD>
+constexpr int fock_dblock_doubles() {
+  return nc(LA) * nc(LB) + nc(LC) * nc(LD) + nc(LA) * nc(LC) + nc(LB) * nc(LD) + nc(LA) * nc(LD) +
+         nc(LB) * nc(LC);
+}
+
 // Run-time purity path.  The compile-time digestion below is specialised for the standard
 // convention (pure iff l >= 2, what BasisSet gives cc-pVXZ / def2 bases); a block whose shells
 // deviate -- Cartesian d of 6-31G* (basis.h.in:368-386), BasisSet::set_pure(false), a pure p
@@ -113,7 +120,8 @@ static __device__ __noinline__ void fock_digest_generic(const GenericDigest g, b
 template <int LA, int LB, int LC, int LD, int T, bool WARP_SYNC>
 __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int lane,
                                             double* __restrict__ fin /* [NAB][CS] */, int,
-                                            double* __restrict__ buf2 /* NAB*NCD dense */, int ib,
+                                            double* __restrict__ buf2 /* NAB*NCD dense */,
+                                            double* __restrict__ dsm /* fock_dblock_doubles */, int ib,
                                             int ik, double deg) {
   constexpr int NA = nc(LA), NB = nc(LB), NC = nc(LC), ND = nc(LD), NCD = NC * ND, CS = NCD | 1;
   constexpr int PA_ = LA >= 2, PB_ = LB >= 2, PC_ = LC >= 2, PD_ = LD >= 2;
@@ -132,8 +140,8 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
       g.pure[0] = p.bra.pure_a; g.pure[1] = p.bra.pure_b; g.pure[2] = p.ket.pure_a; g.pure[3] = p.ket.pure_b;
       g.bf[0] = g.bf[1] = g.bf[2] = g.bf[3] = 0;
       if (active) {
-        const int2 ab = reinterpret_cast<const int2*>(p.bra.bf)[ib];
-        const int2 cd = reinterpret_cast<const int2*>(p.ket.bf)[ik];
+        const int2 ab = *reinterpret_cast<const int2*>(p.bra.geom[ib].bf);
+        const int2 cd = *reinterpret_cast<const int2*>(p.ket.geom[ik].bf);
         g.bf[0] = ab.x; g.bf[1] = ab.y; g.bf[2] = cd.x; g.bf[3] = cd.y;
       }
       fock_digest_generic(g, active, lane, T, WARP_SYNC, fin, CS, buf2, deg);
@@ -202,7 +210,6 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
     }
     sync();
   }
-  if (!active) return;
   const double* cur = (NPASS % 2 == 1) ? buf2 : fin;
   auto I = [&](int a, int b, int c, int d) -> double {
     if constexpr (NPASS > 0)
@@ -210,54 +217,82 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
     else
       return fin_at(a * nb + b, c * nd + d);
   };
-  const int2 bf_ab = reinterpret_cast<const int2*>(p.bra.bf)[ib];   // one 8-byte load per pair
-  const int2 bf_cd = reinterpret_cast<const int2*>(p.ket.bf)[ik];
-  const int bfa = bf_ab.x, bfb = bf_ab.y, bfc = bf_cd.x, bfd = bf_cd.y;
+  int bfa = 0, bfb = 0, bfc = 0, bfd = 0;
+  if (active) {
+    const int2 bf_ab = *reinterpret_cast<const int2*>(p.bra.geom[ib].bf);   // one 8-byte load per pair
+    const int2 bf_cd = *reinterpret_cast<const int2*>(p.ket.geom[ik].bf);
+    bfa = bf_ab.x; bfb = bf_ab.y; bfc = bf_cd.x; bfd = bf_cd.y;
+  }
   const int n = p.nbf;
   const double* __restrict__ D = p.D;
   double* __restrict__ F = p.F;
+  // The six density blocks of the quartet are fetched ONCE, by the quartet's lanes together, into
+  // shared memory: the contractions below read each D element |F block| times, and a scattered
+  // 8-byte global load costs the L1 a wavefront per lane where a shared-memory read of the same
+  // value is a broadcast (Fock-mode ncu: l1tex 90-96 % busy, FP64 pipe 7-15 %).
+  constexpr int O_AB = 0, O_CD = O_AB + na * nb, O_AC = O_CD + nc_ * nd, O_BD = O_AC + na * nc_,
+                O_AD = O_BD + nb * nd, O_BC = O_AD + na * nd, NDB = O_BC + nb * nc_;
+  if (active)
+    for (int i = lane; i < NDB; i += T) {
+      int r, c, r0, c0;
+      if (i < O_CD) { r = i / nb; c = i - r * nb; r0 = bfa; c0 = bfb; }
+      else if (i < O_AC) { const int k = i - O_CD; r = k / nd; c = k - r * nd; r0 = bfc; c0 = bfd; }
+      else if (i < O_BD) { const int k = i - O_AC; r = k / nc_; c = k - r * nc_; r0 = bfa; c0 = bfc; }
+      else if (i < O_AD) { const int k = i - O_BD; r = k / nd; c = k - r * nd; r0 = bfb; c0 = bfd; }
+      else if (i < O_BC) { const int k = i - O_AD; r = k / nd; c = k - r * nd; r0 = bfa; c0 = bfd; }
+      else { const int k = i - O_BC; r = k / nc_; c = k - r * nc_; r0 = bfb; c0 = bfc; }
+      dsm[i] = __ldg(&D[(size_t)(r0 + r) * n + c0 + c]);
+    }
+  sync();
+  if (!active) return;
+  const double* __restrict__ Dab = dsm + O_AB;
+  const double* __restrict__ Dcd = dsm + O_CD;
+  const double* __restrict__ Dac = dsm + O_AC;
+  const double* __restrict__ Dbd = dsm + O_BD;
+  const double* __restrict__ Dad = dsm + O_AD;
+  const double* __restrict__ Dbc = dsm + O_BC;
   for (int i = lane; i < na * nb; i += T) {  // F(a,b) += D(c,d) v
     const int a = i / nb, b = i - a * nb;
     double s = 0.0;
     for (int c = 0; c < nc_; ++c)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfc + c) * n + bfd + d]);
-    atomicAdd(&F[(bfa + a) * n + bfb + b], s * deg);
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dcd[c * nd + d];
+    atomicAdd(&F[(size_t)(bfa + a) * n + bfb + b], s * deg);
   }
   for (int i = lane; i < nc_ * nd; i += T) {  // F(c,d) += D(a,b) v
     const int c = i / nd, d = i - c * nd;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfb + b]);
-    atomicAdd(&F[(bfc + c) * n + bfd + d], s * deg);
+      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * Dab[a * nb + b];
+    atomicAdd(&F[(size_t)(bfc + c) * n + bfd + d], s * deg);
   }
   const double kdeg = -0.25 * deg;
   for (int i = lane; i < na * nc_; i += T) {  // F(a,c) -= 1/4 D(b,d) v
     const int a = i / nc_, c = i - a * nc_;
     double s = 0.0;
     for (int b = 0; b < nb; ++b)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfb + b) * n + bfd + d]);
-    atomicAdd(&F[(bfa + a) * n + bfc + c], s * kdeg);
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dbd[b * nd + d];
+    atomicAdd(&F[(size_t)(bfa + a) * n + bfc + c], s * kdeg);
   }
   for (int i = lane; i < nb * nd; i += T) {  // F(b,d) -= 1/4 D(a,c) v
     const int b = i / nd, d = i - b * nd;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfc + c]);
-    atomicAdd(&F[(bfb + b) * n + bfd + d], s * kdeg);
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dac[a * nc_ + c];
+    atomicAdd(&F[(size_t)(bfb + b) * n + bfd + d], s * kdeg);
   }
   for (int i = lane; i < na * nd; i += T) {  // F(a,d) -= 1/4 D(b,c) v
     const int a = i / nd, d = i - a * nd;
     double s = 0.0;
     for (int b = 0; b < nb; ++b)
-      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * __ldg(&D[(bfb + b) * n + bfc + c]);
-    atomicAdd(&F[(bfa + a) * n + bfd + d], s * kdeg);
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dbc[b * nc_ + c];
+    atomicAdd(&F[(size_t)(bfa + a) * n + bfd + d], s * kdeg);
   }
   for (int i = lane; i < nb * nc_; i += T) {  // F(b,c) -= 1/4 D(a,d) v
     const int b = i / nc_, c = i - b * nc_;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * __ldg(&D[(bfa + a) * n + bfd + d]);
-    atomicAdd(&F[(bfb + b) * n + bfc + c], s * kdeg);
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dad[a * nd + d];
+    atomicAdd(&F[(size_t)(bfb + b) * n + bfc + c], s * kdeg);
   }
 }
 

@@ -104,7 +104,6 @@ extern "C" int lb200_significant_pairs(const lb200_basis* bs, double threshold, 
                         v.O[3 * a + 2] == v.O[3 * b + 2];
       bool sig = same;
       if (!same) {
-        // cheap exact pre-filter: every primitive product is bounded by exp(-rho_min |AB|^2)
         sig = overlap_block_norm(v, a, b) >= threshold;
       }
       if (sig) {

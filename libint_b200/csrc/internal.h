@@ -45,7 +45,7 @@ struct lb200_pairs {
   // host copies (small; used by lb200_pairs_get and the Fock driver)
   std::vector<int> prim_off, shell, bf, p1p2;
   std::vector<lb200::PrimPair> prim;
-  std::vector<double> AB;
+  std::vector<double> AB, Kraw;   // Kraw: K of shell.h:1241-1243 without the coefficient product
   void* d_block = nullptr;  // single allocation backing all device arrays
 };
 

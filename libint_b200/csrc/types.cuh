@@ -9,31 +9,42 @@ constexpr int kBoysOrder = 7;         // degree of the interpolating polynomial
 constexpr int kBoysNInt = 819;        // intervals on [0,117)
 constexpr double kBoysTmax = 117.0;   // above: asymptotic upward recursion
 constexpr int kBoysTableMmax = 24;    // table rows per interval - 1
+constexpr int kPrimCounters = 64;     // profiling counters (EriParams::prim_counter)
 
 // One primitive pair of a shell pair: what ShellPair::PrimPairData holds in the reference
-// (include/libint2/shell.h:1084-1092) plus what Engine::compute2 derives from it per quartet
-// (PA, gamma, c_a*c_b; engine.impl.h:1331-1367,1514-1537), computed once instead.
-struct alignas(16) PrimPair {   // 16-byte aligned: records move as 128-bit loads / cp.async pieces
+// (include/libint2/shell.h:1084-1092) plus gamma and c_a*c_b folded into K (engine.impl.h:1331-1367),
+// computed once instead of per quartet.  64 bytes = half a cache line, 16-byte aligned: a record moves
+// as four 128-bit loads / cp.async pieces and never straddles a line.  PA = P - A is formed in the
+// kernel from the pair's PairGeom (the same subtraction the reference does per quartet,
+// engine.impl.h:1514-1520).
+struct alignas(16) PrimPair {
   double P[3];    // (alpha_a A + alpha_b B)/gamma  (shell.h:1186-1194)
-  double PA[3];   // P - A; exactly 0 when b is the unit shell (3-centre bra, engine.impl.h:1515)
   double Kc;      // sqrt(2) pi^(5/4) exp(-rho |AB|^2)/gamma * c_a * c_b   (shell.h:1241-1243)
   double gamma;   // alpha_a + alpha_b
   double oog;     // 1/gamma
   double ln_scr;  // primitive-pair screening value (shell.h:1162-1165,1214-1232,1288-1290)
   double nonsph;  // nonsph_screen_fac, ScreeningMethod::Conservative only (shell.h:1196-1212)
-  double pad_;
 };
-static_assert(sizeof(PrimPair) == 96, "PrimPair layout");
+static_assert(sizeof(PrimPair) == 64, "PrimPair layout");
+
+// Per shell pair: everything a quartet needs besides the primitive records, in one 64-byte line.
+struct alignas(16) PairGeom {
+  double A[3];    // centre of the first shell
+  double AB[3];   // A - B
+  int bf[2];      // first basis function of each shell
+  int shell[2];   // shell indices (first, second)
+};
+static_assert(sizeof(PairGeom) == 64, "PairGeom layout");
 
 // A block of shell pairs of one class (la >= lb, fixed purity), first shell = higher AM.
 struct PairBlock {
   int npair;
   int la, lb, pure_a, pure_b;
+  int unit_b;              // second shell is Shell::unit(): PA = 0 exactly (engine.impl.h:1515)
   const int* prim_off;     // [npair+1] offsets into prim
   const PrimPair* prim;    // concatenated primitive pairs (screened)
-  const double* AB;        // [npair][3]  A - B
-  const int* shell;        // [npair][2]  shell indices (first, second)
-  const int* bf;           // [npair][2]  first basis function of each shell
+  const PairGeom* geom;    // [npair]
+  const int* shell;        // [npair][2]  shell indices, again, as a dense array for the screening kernel
   const double* schwarz;   // [npair]     sqrt(max|(ab|ab)|)          (Fock build only)
   const int* gidx;         // [npair]     canonical pair index s1(s1+1)/2+s2 (Fock build only)
   int max_nprim;           // largest number of primitive pairs kept by any pair of the block
@@ -71,7 +82,7 @@ struct EriParams {
   int swap_tasks;             // 1: tasks are (ket pair, bra pair) in kernel orientation
   int uncontracted;           // 1: no pair of either block holds more than one primitive pair
   unsigned* work_counter;    // dynamic scheduling counter (zeroed by host)
-  unsigned long long* prim_counter;  // profiling only (else null): surviving primitive quartets
+  unsigned long long* prim_counter;  // profiling only (else null): [kPrimCounters] surviving primitive quartets
   const double* boys;        // [kBoysNInt][kBoysTableMmax+1][8]
   // primitive screening (engine.impl.h:1313-1314,1371-1386)
   int screening;
