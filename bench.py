@@ -539,10 +539,19 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
     G = torch.empty((n, n), dtype=torch.float64, device=dev)
     Gh = torch.empty((n, n), dtype=torch.float64).pin_memory()
 
+    from libint_b200.fock import make_comm
+    comm = make_comm(ctx)   # lb200_comm_create: NCCL behind the C ABI (None on one rank)
+
+    def reduce_(G):
+        if comm is not None:
+            comm.allreduce_(G)   # lb200_fock_allreduce on the context's stream (= `stream`)
+        else:
+            allreduce_sum_(G)
+
     def build():
         with torch.cuda.stream(stream):
             f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
-            allreduce_sum_(G)
+            reduce_(G)
 
     build()  # warm-up
     barrier()
@@ -559,7 +568,7 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
     with torch.cuda.stream(stream):
         Dd.copy_(Dh, non_blocking=True)
         f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
-        allreduce_sum_(G)
+        reduce_(G)
         Gh.copy_(G, non_blocking=True)
     barrier()
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
@@ -604,7 +613,7 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
             "nshell": len(obs), "nbf": n, "significant_pairs": int(len(f.pair_s1)),
             "shell_quartets": nquart, "seconds": sec, "e2e_seconds": e2e_sec,
             "quartets_per_s": nquart / sec, "setup_seconds": setup_s, "n_gpus": world, "scaling": "strong",
-            "allreduce": "nccl sum of nbf^2 f64" if world > 1 else None, "roofline": roof,
+            "allreduce": "lb200_fock_allreduce: ncclAllReduce(sum, f64, nbf^2) on the build stream" if world > 1 else None, "roofline": roof,
             "checksum": float(Gh.abs().sum().item())}
 
 

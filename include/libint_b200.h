@@ -49,6 +49,7 @@ typedef struct lb200_context lb200_context;
 typedef struct lb200_basis lb200_basis;
 typedef struct lb200_pairs lb200_pairs;
 typedef struct lb200_fock lb200_fock;
+typedef struct lb200_comm lb200_comm;
 
 /* ---- library / context life cycle: replaces libint2::initialize()/finalize()
  *      (include/libint2/initialize.h:76-136) and Engine construction (engine.h:503-526). */
@@ -163,6 +164,22 @@ int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks);
 int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double precision,
                      int use_schwarz, int rank, int nranks, double* G, int G_on_device,
                      double* stats);
+
+/* ---- multi-GPU: one process per GPU, each builds the partial G of the bra rows it owns
+ *      (lb200_fock_build with rank / nranks), then one in-place ncclAllReduce(sum, f64) over NVLink
+ *      combines them -- the GPU form of the reference's sum over thread-private G's
+ *      (hartree-fock++.cc:1753-1755).  NCCL is bound at run time (the library does not link it).
+ *        id = lb200_comm_unique_id() on rank 0 (128 bytes, ncclUniqueId), distributed by the host's own
+ *        means (MPI_Bcast, a file, torch.distributed ...), then lb200_comm_create on every rank; or wrap a
+ *        communicator the host already has (ncclComm_t cast to void*) with lb200_comm_from_nccl.
+ *      lb200_fock_allreduce runs on the context's stream (asynchronous, like every device-buffer call). */
+int lb200_comm_unique_id(char* id, int cap /* >= 128 */);
+int lb200_comm_create(lb200_context* ctx, int nranks, int rank, const char* id, lb200_comm** out);
+int lb200_comm_from_nccl(lb200_context* ctx, void* nccl_comm, lb200_comm** out);
+int lb200_comm_destroy(lb200_comm* c);
+int lb200_comm_rank(const lb200_comm* c);
+int lb200_comm_size(const lb200_comm* c);
+int lb200_fock_allreduce(lb200_comm* c, double* G_device, long long count);
 
 /* Profiling of the build (no reference counterpart): with profiling on, every (bra class, ket class,
  * contraction buckets) launch of the next builds is timed with CUDA events (one stream sync per

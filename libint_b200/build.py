@@ -69,8 +69,7 @@ def build(jobs=None, force=False, verbose=False):
             if verbose and out.strip():
                 print(out)
     if jobs_list or not os.path.exists(LIB):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets", "-lcudart_static"]
-             if False else [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets"])
+        _run([NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets", "-ldl"])
     build_iface(force=bool(jobs_list) or force)
     return LIB
 

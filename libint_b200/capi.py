@@ -61,6 +61,13 @@ SIGNATURES = {
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_comm_unique_id": (C.c_int, [C.c_char_p, C.c_int]),
+    "lb200_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "lb200_comm_from_nccl": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "lb200_comm_destroy": (C.c_int, [vp]),
+    "lb200_comm_rank": (C.c_int, [vp]),
+    "lb200_comm_size": (C.c_int, [vp]),
+    "lb200_fock_allreduce": (C.c_int, [vp, vp, C.c_longlong]),
     "lb200_fock_set_profile": (C.c_int, [vp, C.c_int]),
     "lb200_fock_get_profile": (C.c_longlong, [vp, dp, C.c_longlong]),
     "lb200_fock_task_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
@@ -324,6 +331,42 @@ class Fock:
     def close(self):
         if self.h:
             load().lb200_fock_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """NCCL communicator behind the C ABI (lb200_comm_*): the all-reduce of partial Fock matrices."""
+
+    def __init__(self, ctx, nranks, rank, unique_id):
+        self.ctx = ctx
+        h = vp()
+        ctx.check(load().lb200_comm_create(ctx.h, int(nranks), int(rank), bytes(unique_id), C.byref(h)),
+                  "comm_create")
+        self.h = h
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        n = load().lb200_comm_unique_id(buf, 128)
+        if n < 0:
+            raise Lb200Error("lb200_comm_unique_id failed (%d): NCCL not available" % n)
+        return buf.raw
+
+    def allreduce_(self, G):
+        """in-place sum over ranks of a torch CUDA float64 tensor, on the context's stream"""
+        self.ctx.check(load().lb200_fock_allreduce(self.h, vp(G.data_ptr()), G.numel()), "fock_allreduce")
+        return G
+
+    def close(self):
+        if self.h:
+            load().lb200_comm_destroy(self.h)
             self.h = None
 
     def __del__(self):

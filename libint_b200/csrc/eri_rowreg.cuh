@@ -495,8 +495,9 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
           });
         }
       } else {
-        if constexpr (FOCK && LB200_BOYS_RECUR) {
-          // one lane per quartet evaluates every order from one table row (boys_all)
+        if constexpr (FOCK && LB200_BOYS_RECUR && NEC <= 4) {
+          // one lane per quartet evaluates every order from one table row (boys_all); with more rows
+          // per quartet the row-per-lane evaluation is already spread thin enough
           if (lane_on && rmeta.row == 0) {
             double Fa[L + 1];
             if (on) boys_all<L>(p.boys, Targ, Fa);

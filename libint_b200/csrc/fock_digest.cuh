@@ -14,6 +14,9 @@ namespace lb200 {
 // doubles of shared memory fock_digest needs for the staged density blocks (Cartesian upper bound)
 template <int LA, int LB, int LC, int LD>
 constexpr int fock_dblock_doubles() {
+#if !defined(LB200_DIGEST_STAGE) || !LB200_DIGEST_STAGE
+  return 0;
+#endif
   return nc(LA) * nc(LB) + nc(LC) * nc(LD) + nc(LA) * nc(LC) + nc(LB) * nc(LD) + nc(LA) * nc(LD) +
          nc(LB) * nc(LC);
 }
@@ -230,8 +233,13 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
   // shared memory: the contractions below read each D element |F block| times, and a scattered
   // 8-byte global load costs the L1 a wavefront per lane where a shared-memory read of the same
   // value is a broadcast (Fock-mode ncu: l1tex 90-96 % busy, FP64 pipe 7-15 %).
+#ifndef LB200_DIGEST_STAGE
+#define LB200_DIGEST_STAGE 0
+#endif
+  constexpr bool STAGE = LB200_DIGEST_STAGE && T > 1;
   constexpr int O_AB = 0, O_CD = O_AB + na * nb, O_AC = O_CD + nc_ * nd, O_BD = O_AC + na * nc_,
                 O_AD = O_BD + nb * nd, O_BC = O_AD + na * nd, NDB = O_BC + nb * nc_;
+  if constexpr (STAGE) {
   if (active)
     for (int i = lane; i < NDB; i += T) {
       int r, c, r0, c0;
@@ -244,25 +252,27 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
       dsm[i] = __ldg(&D[(size_t)(r0 + r) * n + c0 + c]);
     }
   sync();
+  }
   if (!active) return;
-  const double* __restrict__ Dab = dsm + O_AB;
-  const double* __restrict__ Dcd = dsm + O_CD;
-  const double* __restrict__ Dac = dsm + O_AC;
-  const double* __restrict__ Dbd = dsm + O_BD;
-  const double* __restrict__ Dad = dsm + O_AD;
-  const double* __restrict__ Dbc = dsm + O_BC;
+  // element (r, c) of a density block: from the staged copy, or straight from global memory
+  auto Dab = [&](int a, int b) { return STAGE ? dsm[O_AB + a * nb + b] : __ldg(&D[(size_t)(bfa + a) * n + bfb + b]); };
+  auto Dcd = [&](int c, int d) { return STAGE ? dsm[O_CD + c * nd + d] : __ldg(&D[(size_t)(bfc + c) * n + bfd + d]); };
+  auto Dac = [&](int a, int c) { return STAGE ? dsm[O_AC + a * nc_ + c] : __ldg(&D[(size_t)(bfa + a) * n + bfc + c]); };
+  auto Dbd = [&](int b, int d) { return STAGE ? dsm[O_BD + b * nd + d] : __ldg(&D[(size_t)(bfb + b) * n + bfd + d]); };
+  auto Dad = [&](int a, int d) { return STAGE ? dsm[O_AD + a * nd + d] : __ldg(&D[(size_t)(bfa + a) * n + bfd + d]); };
+  auto Dbc = [&](int b, int c) { return STAGE ? dsm[O_BC + b * nc_ + c] : __ldg(&D[(size_t)(bfb + b) * n + bfc + c]); };
   for (int i = lane; i < na * nb; i += T) {  // F(a,b) += D(c,d) v
     const int a = i / nb, b = i - a * nb;
     double s = 0.0;
     for (int c = 0; c < nc_; ++c)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dcd[c * nd + d];
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dcd(c, d);
     atomicAdd(&F[(size_t)(bfa + a) * n + bfb + b], s * deg);
   }
   for (int i = lane; i < nc_ * nd; i += T) {  // F(c,d) += D(a,b) v
     const int c = i / nd, d = i - c * nd;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * Dab[a * nb + b];
+      for (int b = 0; b < nb; ++b) s += I(a, b, c, d) * Dab(a, b);
     atomicAdd(&F[(size_t)(bfc + c) * n + bfd + d], s * deg);
   }
   const double kdeg = -0.25 * deg;
@@ -270,28 +280,28 @@ __device__ __forceinline__ void fock_digest(const EriParams& p, bool active, int
     const int a = i / nc_, c = i - a * nc_;
     double s = 0.0;
     for (int b = 0; b < nb; ++b)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dbd[b * nd + d];
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dbd(b, d);
     atomicAdd(&F[(size_t)(bfa + a) * n + bfc + c], s * kdeg);
   }
   for (int i = lane; i < nb * nd; i += T) {  // F(b,d) -= 1/4 D(a,c) v
     const int b = i / nd, d = i - b * nd;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dac[a * nc_ + c];
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dac(a, c);
     atomicAdd(&F[(size_t)(bfb + b) * n + bfd + d], s * kdeg);
   }
   for (int i = lane; i < na * nd; i += T) {  // F(a,d) -= 1/4 D(b,c) v
     const int a = i / nd, d = i - a * nd;
     double s = 0.0;
     for (int b = 0; b < nb; ++b)
-      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dbc[b * nc_ + c];
+      for (int c = 0; c < nc_; ++c) s += I(a, b, c, d) * Dbc(b, c);
     atomicAdd(&F[(size_t)(bfa + a) * n + bfd + d], s * kdeg);
   }
   for (int i = lane; i < nb * nc_; i += T) {  // F(b,c) -= 1/4 D(a,d) v
     const int b = i / nc_, c = i - b * nc_;
     double s = 0.0;
     for (int a = 0; a < na; ++a)
-      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dad[a * nd + d];
+      for (int d = 0; d < nd; ++d) s += I(a, b, c, d) * Dad(a, d);
     atomicAdd(&F[(size_t)(bfb + b) * n + bfc + c], s * kdeg);
   }
 }

@@ -99,7 +99,15 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
       return launch_rowreg<LA, LB, LC, LD, MODE>(p, rows, num_sms, stream);
     }
   }
-  if constexpr (LA + LB <= 4) {
+  // Fock mode, (fd| / (ff| against an (ss| or (ps| pair: the small pair still provides the rows and the
+  // big pair is unrolled (register pyramid of depth 5 / 6, partly in local memory).  With rows = the
+  // big pair these classes ran 56 / 84 lanes per quartet through CTA-wide barriers at < 1 % of the
+  // FP64 peak (profiles/r02a_ncu_fock_3210.txt, _3300.txt).
+#ifndef LB200_ROWS_SMALL_MAXE
+#define LB200_ROWS_SMALL_MAXE 1
+#endif
+  constexpr bool ROWS_SMALL = LA + LB <= 4 || (MODE == kModeFock && LC + LD <= LB200_ROWS_SMALL_MAXE);
+  if constexpr (ROWS_SMALL) {
     // rows = (LC LD| (the smaller pair), (LA LB) unrolled: the kernel sees bra and ket swapped
     EriParams q = p;
     q.bra = p.ket;

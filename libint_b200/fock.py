@@ -47,6 +47,19 @@ def allreduce_sum_(G):
     return G
 
 
+def make_comm(ctx):
+    """NCCL communicator of the C ABI (lb200_comm_create) for the ranks of the current
+    torch.distributed job: rank 0's ncclUniqueId travels over the process group that torchrun set up
+    (plumbing only); the all-reduce itself is lb200_fock_allreduce.  None on a single rank."""
+    import torch.distributed as dist
+    rank, world, _ = dist_env()
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return None
+    box = [capi.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return capi.Comm(ctx, world, rank, box[0])
+
+
 class FockBuilder:
     def __init__(self, obs, ctx=None, device=None, pair_threshold=1e-12, rank=None, nranks=None):
         r, w, local = dist_env()
@@ -59,6 +72,7 @@ class FockBuilder:
         self.basis = capi.Basis(ctx, *self.obs.flat())
         self.fock = capi.Fock(ctx, self.basis, threshold=pair_threshold)
         self.nbf = self.basis.nbf
+        self.comm = None   # created on first use (needs a GPU and an initialised process group)
 
     def schwarz(self):
         return self.fock.schwarz()
@@ -79,5 +93,11 @@ class FockBuilder:
         G = torch.empty((self.nbf, self.nbf), dtype=torch.float64, device=dev)
         self.ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         self.build_partial(Dt, precision, out=G, use_schwarz=use_schwarz)
-        allreduce_sum_(G)
+        if self.nranks > 1:
+            if self.comm is None:
+                self.comm = make_comm(self.ctx)
+            if self.comm is not None:
+                self.comm.allreduce_(G)      # ncclAllReduce on the context's (= torch's current) stream
+            else:
+                allreduce_sum_(G)
         return G

@@ -15,6 +15,7 @@ n = obs.nbf
 rng = np.random.default_rng(7)
 C = rng.standard_normal((n, max(1, n // 8))) / np.sqrt(n)
 D = C @ C.T
+f.build(D, prec)   # warm-up: lazy module load, local-memory pool, allocations
 t0 = time.time(); G, st = f.build(D, prec, stats=True)
 print("build: wall %.2f s, device %.2f s, %.4e shell quartets (%.3e /s), %d launches, %.3e candidates; |G|_1 = %.10e; symmetric %s"
       % (time.time() - t0, st["ms"] * 1e-3, st["nquartets"], st["nquartets"] / (st["ms"] * 1e-3), st["launches"], st["candidates"], np.abs(G).sum(), np.array_equal(G, G.T)), flush=True)
