@@ -61,7 +61,8 @@ struct RR {
   // Fock mode: final integrals [NAB][CS] at HDR, then a second buffer used first as the
   // row->column transpose buffer and afterwards by the cart->pure passes
   static constexpr int OFF_B2 = HDR + NAB * CS;
-  static constexpr int OFF_D = OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0);  // staged density blocks
+  // staged density blocks: written (cp.async) while the K loop runs, so clear of its area too
+  static constexpr int OFF_D = cmax(OFF_B2 + cmax(NAB * NCD, LB > 0 ? NCD * RTP : 0), (PRIM_DOUBLES + 1) & ~1);
   static constexpr int FOCK_DOUBLES = OFF_D + fock_dblock_doubles<LA, LB, LC, LD>();
   static constexpr int STORE_DOUBLES = OFF_B2 + (LB > 0 ? NCD * RTP : 0);
   // Stride between the regions of consecutive quartets.  The lanes of a warp that belong to
@@ -382,11 +383,21 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       }
     }
     const bool bra_unit = p.bra.unit_b != 0, ket_unit = p.ket.unit_b != 0;
+    int bf4[4] = {0, 0, 0, 0};   // first basis functions of the four shells (Fock mode)
+    if constexpr (FOCK) {
+      if (valid) {
+        const int2 ab = *reinterpret_cast<const int2*>(p.bra.geom[ib].bf);
+        const int2 cd = *reinterpret_cast<const int2*>(p.ket.geom[ik].bf);
+        bf4[0] = ab.x; bf4[1] = ab.y; bf4[2] = cd.x; bf4[3] = cd.y;
+      }
+    }
     const double npbraket = (double)nb * (double)nk;
     double acc[K::NFT];
     static_for<K::NFT>([&](auto ic) { acc[decltype(ic)::value] = 0.0; });
     int nsurv = 0;
     sync();   // also separates the previous round's phase 2 from this round's writes
+    if constexpr (FOCK)   // density blocks of this quartet: in flight during the K loop
+      fock_prefetch_density<LA, LB, LC, LD, NEC>(p, valid, rmeta.row, Q + K::OFF_D, bf4);
     int maxit;
     if constexpr (NEC == 1) maxit = nit;   // no exchange inside the loop: private trip count
     else if constexpr (WL) maxit = __reduce_max_sync(0xffffffffu, valid ? nit : 0);
@@ -670,7 +681,7 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       } else {
         // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet --------
         fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && !screened_out, rmeta.row, Q + K::HDR, K::CS,
-                                         Q + K::OFF_B2, Q + K::OFF_D, ib, ik, deg);
+                                         Q + K::OFF_B2, Q + K::OFF_D, ib, ik, deg, bf4);
       }
     }
   }

@@ -25,18 +25,6 @@
 
 namespace lb200 {
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
 // TR: the caller's bra is this kernel's unrolled side, results leave as [cd][ab] through the
 // transposing copy-out.  TR = false with LB > 0 stores straight from the bra-HRR lanes and needs
 // no staging buffer for the final integrals: a third less shared memory, one more CTA per SM.
@@ -70,7 +58,8 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int OFF_FIN = PIPE;                       // final integrals [NAB][CS]
   static constexpr bool HAS_FIN = TR || LB == 0 || FOCK;
   static constexpr int OFF_B2 = OFF_FIN + (HAS_FIN ? B::NAB * B::CS : 0);  // row -> column transpose buffer
-  static constexpr int OFF_D = OFF_B2 + cmax(FOCK ? B::NAB * B::NCD : 0, LB > 0 ? B::NCD * B::RTP : 0);
+  static constexpr int OFF_D =
+      cmax(OFF_B2 + cmax(FOCK ? B::NAB * B::NCD : 0, LB > 0 ? B::NCD * B::RTP : 0), (VRR_DOUBLES + 1) & ~1);
   static constexpr int P2_DOUBLES = OFF_D + (FOCK ? fock_dblock_doubles<LA, LB, LC, LD>() : 0);
   static constexpr int QSIZE = B::pad_stride(cmax(VRR_DOUBLES, P2_DOUBLES));
 #ifndef LB200_PRIM_MINB_HI
@@ -291,6 +280,16 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     // ---- prerequisites from the stage (engine.impl.h:1331-1367,1389-1392,1602-1641) --------
     const bool on = S[K::S_PREP + 2] != 0.0;
+    int bf4[4] = {0, 0, 0, 0};
+    if constexpr (FOCK) {   // density blocks of this quartet: in flight during the VRR
+      const bool act = lane_on && base + qg < ntasks && on;
+      if (act) {
+        const int2 ab = *reinterpret_cast<const int2*>(S + K::S_GB + 6);
+        const int2 cd = *reinterpret_cast<const int2*>(S + K::S_GK + 6);
+        bf4[0] = ab.x; bf4[1] = ab.y; bf4[2] = cd.x; bf4[3] = cd.y;
+      }
+      fock_prefetch_density<LA, LB, LC, LD, NEC>(p, act, rmeta.row, Q + K::OFF_D, bf4);
+    }
     double PA[3], WP[3], QC[3], WQ[3], oo2z, roz, koo2e[6], roe, ce[3];
     {
       const double oogpq = S[K::S_PREP + 0], rho = S[K::S_PREP + 1];
@@ -443,7 +442,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     if constexpr (FOCK) {
       // ---- cart -> pure, then 6-way digestion, by the NEC lanes of each quartet ------------
       fock_digest<LA, LB, LC, LD, NEC, WL>(p, valid && on, rmeta.row, Q + K::OFF_FIN, K::CS,
-                                           Q + K::OFF_B2, Q + K::OFF_D, ocur.ib, ocur.ik, deg_cur);
+                                           Q + K::OFF_B2, Q + K::OFF_D, ocur.ib, ocur.ik, deg_cur, bf4);
     } else {
       // ---- coalesced copy-out (see eri_rowreg.cuh) ----------------------------------------
       constexpr int BLK = K::NAB * K::NCD;
