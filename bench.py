@@ -105,9 +105,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # CPU reference legs (oracle = reference Engine on restated kernels; see oracle/)
 # --------------------------------------------------------------------------------------
-def cpu_sweep(classes, npairs, budget_s, nthreads, check=None):
+def cpu_sweep(classes, npairs, budget_s, nthreads, fast=True, use_pairs=True):
     """times the reference Engine (one per thread, round-robin) on a bounded sample of every
-    class; returns the equal-count-mix throughput, per-class rates and the sample text."""
+    class; returns the equal-count-mix throughput, per-class rates and the sample text.
+    fast / use_pairs: the -O3 -march=x86-64-v3 build of the oracle and precomputed ShellPairs handed to
+    compute2 (as hartree-fock++.cc:1697 does) -- the honest baseline; False/False reproduces round 1's
+    (-O2 x86-64-v2, ShellPair::init inside every compute2 call)."""
     from oracle import pyoracle as po
     from libint_b200.flops import quartet_flops
     per = {}
@@ -122,13 +125,16 @@ def cpu_sweep(classes, npairs, budget_s, nthreads, check=None):
         b = rng.integers(0, npairs, nq)
         k = rng.integers(0, npairs, nq)
         q4 = np.stack([b, npairs + b, 2 * npairs + k, 3 * npairs + k], axis=1).astype(np.int32)
-        t, _ = po.time_quartets(sh, q4, nthreads)
+        t, _ = po.time_quartets(sh, q4, nthreads, use_pairs=use_pairs, fast=fast)
         per["".join(map(str, cl))] = nq / t
         tot_q += nq
         tot_t += t
     # equal count per class, as the GPU step: time for one quartet of each class
     mix = len(classes) / sum(1.0 / r for r in per.values())
-    return mix, per, "equal-count mix over %d classes, %d quartets timed in %.1f s" % (len(classes), tot_q, tot_t)
+    return mix, per, ("equal-count mix over %d classes, %d quartets timed in %.1f s; oracle build %s, ShellPairs %s"
+                      % (len(classes), tot_q, tot_t,
+                         "-O3 -march=x86-64-v3" if (fast and po.fast_available()) else "-O2 -march=x86-64-v2",
+                         "precomputed" if use_pairs else "rebuilt per quartet"))
 
 
 def reference_arm(args):
@@ -182,6 +188,8 @@ def main():
     ap.add_argument("--fock-waters", default="4,4,4")
     ap.add_argument("--fock-basis", default="def2-tzvp")
     ap.add_argument("--fock-precision", type=float, default=1e-10)
+    ap.add_argument("--fock256", choices=["auto", "on", "off"], default="auto",
+                    help="configs[4], (H2O)_256 / cc-pVTZ: auto = when running on >= 2 GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-df3c", action="store_true")
     ap.add_argument("--df3c-carbons", type=int, default=40)
@@ -363,6 +371,17 @@ def main():
         except capi.Lb200Error as e:
             fock = {"error": str(e)}
 
+    # ---- configs[4]: (H2O)_256 / cc-pVTZ direct J/K build sharded over the ranks + Fock all-reduce.  On by
+    # default for N >= 2 (one rank needs ~100 s per build; --fock256 forces it at N = 1).
+    fock256 = None
+    if args.fock256 == "on" or (args.fock256 == "auto" and world >= 2 and not args.no_fock):
+        try:
+            fock256 = run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_, fp64_peak,
+                               waters="8,8,4", basis="cc-pvtz", warm=False, e2e=False, profile=world >= 4,
+                               cpu_leg=False)
+        except capi.Lb200Error as e:
+            fock256 = {"error": str(e)}
+
     # ---- 3-centre (P|mu nu) class sweep (configs[3]): C40H82, def2-TZVP / def2-universal-JKFIT -
     df3c = None
     if not args.no_df3c:
@@ -380,14 +399,24 @@ def main():
                        "l2_policy": "outputs (%.1f GB per class) exceed L2; pair tables are L2-resident by design"
                                     % (8 * max_blk * chunk / 1e9)},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "per_class": per, "fock": fock, "df3c": df3c}
+            "per_class": per, "fock": fock, "fock256": fock256, "df3c": df3c,
+            # the strong-scaled half of the metric as top-level numbers: seconds per Fock build at this N
+            "fock_build_seconds": fock.get("seconds") if isinstance(fock, dict) else None,
+            "fock256_build_seconds": fock256.get("seconds") if isinstance(fock256, dict) else None}
 
     if rank == 0 and not args.no_cpu_baseline:
         line["parity"] = sweep_parity(ctx, work, args.npairs, args.parity_quartets)
         ncores = os.cpu_count() or 1
         mix, cper, sample = cpu_sweep(classes, args.npairs, args.cpu_seconds, ncores)
+        # round 1's softer baseline once, so the effect of the two changes is visible
+        mix_r1, _, sample_r1 = cpu_sweep(classes, args.npairs, min(5.0, args.cpu_seconds), ncores, fast=False,
+                                         use_pairs=False)
         line["cpu_baseline"] = {"value": mix, "unit": UNIT, "cores": ncores, "kind": "port",
-                                "sample": sample, "per_class_quartets_per_s": cper}
+                                "sample": sample, "per_class_quartets_per_s": cper,
+                                "round1_method": {"value": mix_r1, "sample": sample_r1},
+                                "note": "reference libint2::Engine (its own headers) on run-time-loop restated "
+                                        "kernels: stock generated libint (unrolled, CSE'd) is faster per quartet; "
+                                        "the generator cannot be built in this image (DESIGN.md section 2)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -519,13 +548,18 @@ def fock_roofline(f, fp64_peak, build_seconds, pure_basis=True):
             "classes": len(out), "top_classes": out[:12]}
 
 
-def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_, fp64_peak=None):
+def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_, fp64_peak=None,
+             waters=None, basis=None, warm=True, e2e=True, profile=True, cpu_leg=True):
+    """One strong-scaled direct Fock build (quartets sharded over the ranks by bra row, partial G's summed
+    by lb200_fock_allreduce inside the timed region): configs[2] by default, configs[4] with
+    waters="8,8,4", basis="cc-pvtz"."""
     import torch
     from libint_b200 import capi
     from libint_b200.basis import BasisSet, water_cluster
-    nx, ny, nz = [int(x) for x in args.fock_waters.split(",")]
+    basis = basis or args.fock_basis
+    nx, ny, nz = [int(x) for x in (waters or args.fock_waters).split(",")]
     atoms = water_cluster(nx, ny, nz)
-    obs = BasisSet(args.fock_basis, atoms)
+    obs = BasisSet(basis, atoms)
     t0 = time.perf_counter()
     B = capi.Basis(ctx, *obs.flat())
     f = capi.Fock(ctx, B)
@@ -553,7 +587,8 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
             f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
             reduce_(G)
 
-    build()  # warm-up
+    if warm:
+        build()  # warm-up
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -563,21 +598,31 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
     barrier()
     sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     # end to end from host D to host G
-    barrier()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        Dd.copy_(Dh, non_blocking=True)
-        f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
-        reduce_(G)
-        Gh.copy_(G, non_blocking=True)
-    barrier()
-    e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    f.set_profile(True)
-    _, st = f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G, stats=True)
-    f.set_profile(False)
-    roof = fock_roofline(f, fp64_peak, sec) if fp64_peak else None
-    nquart = st["nquartets"]
-    if world > 1:
+    e2e_sec = None
+    if e2e:
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            Dd.copy_(Dh, non_blocking=True)
+            f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G)
+            reduce_(G)
+            Gh.copy_(G, non_blocking=True)
+        barrier()
+        e2e_sec = max_over_ranks(time.perf_counter() - t0)
+    else:
+        with torch.cuda.stream(stream):
+            Gh.copy_(G, non_blocking=True)
+        barrier()
+    roof = None
+    if profile:
+        f.set_profile(True)
+        _, st = f.build(Dd, args.fock_precision, rank=rank, nranks=world, out=G, stats=True)
+        f.set_profile(False)
+        roof = fock_roofline(f, fp64_peak, sec) if fp64_peak else None
+        nquart = st["nquartets"]
+    else:
+        nquart = float("nan")
+    if world > 1 and profile:
         t = torch.tensor([nquart], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(t)
         nquart = float(t.item())
@@ -587,9 +632,9 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
     # workload -- an (H2O)_8 sub-cluster of the same lattice and basis -- and the GPU is timed on
     # that sub-cluster as well.
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and cpu_leg:
         from oracle import pyoracle as po
-        obs8 = BasisSet(args.fock_basis, water_cluster(2, 2, 2))
+        obs8 = BasisSet(basis, water_cluster(2, 2, 2))
         B8 = capi.Basis(ctx, *obs8.flat())
         f8 = capi.Fock(ctx, B8)
         C8 = rng.standard_normal((obs8.nbf, max(1, obs8.nbf // 8))) / np.sqrt(obs8.nbf)
@@ -599,20 +644,22 @@ def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allre
         G8, st8 = f8.build(D8, args.fock_precision, stats=True)
         gpu8_s = st8["ms"] * 1e-3
         ncores = os.cpu_count() or 1
-        of = po.Fock(po.Shells(*obs8.flat(), raw=False), f8.pair_s1, f8.pair_s2, nthreads=ncores)
+        # timing build of the oracle (-O3, AVX2+FMA) with the reference's precomputed SchwarzInf ShellPairs
+        of = po.Fock(po.Shells(*obs8.flat(), raw=False), f8.pair_s1, f8.pair_s2, nthreads=ncores, fast=True)
         Gc, stc = of.build(D8, args.fock_precision)
         err = float(np.max(np.abs(G8 - Gc) - 1e-12 * np.abs(Gc)))
         cpu = {"value": stc["nquartets"] / stc["seconds"], "unit": "shell quartets/s", "cores": ncores,
-               "kind": "port", "seconds": stc["seconds"],
-               "sample": "(H2O)_8 / %s sub-cluster, full build, %d shell quartets" % (args.fock_basis, int(stc["nquartets"])),
+               "kind": "port", "seconds": stc["seconds"], "build": "-O3 -march=x86-64-v3" if po.fast_available() else "-O2 -march=x86-64-v2",
+               "sample": "(H2O)_8 / %s sub-cluster, full build, %d shell quartets" % (basis, int(stc["nquartets"])),
                "gpu_seconds_same_sample": gpu8_s, "gpu_quartets_per_s_same_sample": st8["nquartets"] / gpu8_s,
                "max_abs_err_beyond_1e-12_rel": err}
     return {"cpu_baseline": cpu,
             "workload": "(H2O)_%d / %s direct Fock (J - K/2), Schwarz x density screened at %g"
-                        % (nx * ny * nz, args.fock_basis, args.fock_precision),
+                        % (nx * ny * nz, basis, args.fock_precision),
             "nshell": len(obs), "nbf": n, "significant_pairs": int(len(f.pair_s1)),
             "shell_quartets": nquart, "seconds": sec, "e2e_seconds": e2e_sec,
             "quartets_per_s": nquart / sec, "setup_seconds": setup_s, "n_gpus": world, "scaling": "strong",
+            "timed_builds": 1, "warmup_builds": 1 if warm else 0,
             "allreduce": "lb200_fock_allreduce: ncclAllReduce(sum, f64, nbf^2) on the build stream" if world > 1 else None, "roofline": roof,
             "checksum": float(Gh.abs().sum().item())}
 
