@@ -50,6 +50,7 @@ typedef struct lb200_basis lb200_basis;
 typedef struct lb200_pairs lb200_pairs;
 typedef struct lb200_fock lb200_fock;
 typedef struct lb200_comm lb200_comm;
+typedef struct lb200_df3c lb200_df3c;
 
 /* ---- library / context life cycle: replaces libint2::initialize()/finalize()
  *      (include/libint2/initialize.h:76-136) and Engine construction (engine.h:503-526). */
@@ -164,6 +165,31 @@ int lb200_fock_task_owner(int bra_pair_index, int ket_pair_index, int nranks);
 int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double precision,
                      int use_schwarz, int rank, int nranks, double* G, int G_on_device,
                      double* stats);
+
+/* ---- batched Engine::compute2 over an implicit Cartesian product of pair ranges: task t =
+ *      (bra pair b0 + t / nk, ket pair k0 + t % nk), t < nb * nk -- no task list is built or read
+ *      (the three-centre sweep and the two-centre metric are such products).  Device output only. */
+int lb200_eri_product(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket, int b0, int nb,
+                      int k0, int nk, int screening, double precision, int pure_out, double* out_device);
+
+/* ---- density fitting: three-centre integrals (P|mu nu) as dense slabs and the two-centre metric (P|Q):
+ *      the DF set-up of tests/hartree-fock/hartree-fock++.cc:2215-2262 (Zxy[ndf][n][n] via
+ *      Engine::compute2<coulomb, xs_xx>(dfbs[s1], Shell::unit(), obs[s2], obs[s3])) and
+ *      compute_2body_2index_ints (:1517-1571).
+ *      create: obs pairs (s1 >= s2) = the significant orbital shell pairs (lb200_significant_pairs).
+ *      slab:   Z[P - first][mu][nu] (device, row-major, pure where flagged, both (mu,nu) and (nu,mu)) for the
+ *              functions of DF shells [P0, P0 + nP); zeroed first.  threshold > 0 drops triplets whose
+ *              Schwarz-type bound sqrt|(P|P)| sqrt|(mu nu|mu nu)| is below it (the reference computes all);
+ *              precision as in lb200_eri_batch.  stats (optional, 2 doubles): triplets computed, triplets total.
+ *              Slabs of disjoint shell ranges are independent: ranks shard by DF shell, no collective.
+ *      metric: V[ndf][ndf] (device).   info[0..5] = nbf, ndf, DF shells, orbital pairs, shell triplets, groups. */
+int lb200_df3c_create(lb200_context* ctx, const lb200_basis* obs, const lb200_basis* dfbs, long long npair,
+                      const int* s1, const int* s2, lb200_df3c** out);
+int lb200_df3c_destroy(lb200_df3c* f);
+int lb200_df3c_slab(lb200_df3c* f, int P0, int nP, double threshold, double precision, double* Z_device,
+                    double* stats);
+int lb200_df3c_metric(lb200_df3c* f, double* V_device);
+int lb200_df3c_info(const lb200_df3c* f, long long* info);
 
 /* ---- multi-GPU: one process per GPU, each builds the partial G of the bra rows it owns
  *      (lb200_fock_build with rank / nranks), then one in-place ncclAllReduce(sum, f64) over NVLink

@@ -61,6 +61,12 @@ SIGNATURES = {
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_eri_product": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]),
+    "lb200_df3c_create": (C.c_int, [vp, vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
+    "lb200_df3c_destroy": (C.c_int, [vp]),
+    "lb200_df3c_slab": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, dp]),
+    "lb200_df3c_metric": (C.c_int, [vp, vp]),
+    "lb200_df3c_info": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "lb200_comm_unique_id": (C.c_int, [C.c_char_p, C.c_int]),
     "lb200_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]),
     "lb200_comm_from_nccl": (C.c_int, [vp, vp, C.POINTER(vp)]),
@@ -331,6 +337,55 @@ class Fock:
     def close(self):
         if self.h:
             load().lb200_fock_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eri_product(ctx, bra, ket, b0, nb, k0, nk, out, screening=SCREEN_ORIGINAL, precision=0.0, pure_out=False):
+    """Engine::compute2 over the implicit product (bra pairs [b0, b0+nb)) x (ket pairs [k0, k0+nk)) into the
+    torch CUDA tensor `out`."""
+    ctx.check(load().lb200_eri_product(ctx.h, bra.h, ket.h, int(b0), int(nb), int(k0), int(nk), int(screening),
+                                       float(precision), int(pure_out), vp(out.data_ptr())), "eri_product")
+    return out
+
+
+class Df3c:
+    """(P|mu nu) slabs and the (P|Q) metric on the GPU (lb200_df3c_*)."""
+
+    def __init__(self, ctx, obs, dfbs, pair_s1=None, pair_s2=None, threshold=1e-12):
+        self.ctx, self.obs, self.dfbs = ctx, obs, dfbs
+        if pair_s1 is None:
+            pair_s1, pair_s2 = significant_pairs(obs, threshold)
+        self.pair_s1 = np.ascontiguousarray(pair_s1, dtype=np.int32)
+        self.pair_s2 = np.ascontiguousarray(pair_s2, dtype=np.int32)
+        h = vp()
+        ctx.check(load().lb200_df3c_create(ctx.h, obs.h, dfbs.h, len(self.pair_s1), _i(self.pair_s1),
+                                           _i(self.pair_s2), C.byref(h)), "df3c_create")
+        self.h = h
+        info = (C.c_longlong * 6)()
+        load().lb200_df3c_info(h, info)
+        self.nbf, self.ndf, self.ndfshell, self.npairs, self.ntriplets, self.ngroups = [int(x) for x in info]
+
+    def slab(self, Z, P0, nP, threshold=0.0, precision=0.0):
+        """fills the torch CUDA float64 tensor Z[nPfun, nbf, nbf] for DF shells [P0, P0+nP); returns
+        (triplets computed, triplets total)"""
+        st = np.zeros(2)
+        self.ctx.check(load().lb200_df3c_slab(self.h, int(P0), int(nP), float(threshold), float(precision),
+                                              vp(Z.data_ptr()), _d(st)), "df3c_slab")
+        return st[0], st[1]
+
+    def metric(self, V):
+        self.ctx.check(load().lb200_df3c_metric(self.h, vp(V.data_ptr())), "df3c_metric")
+        return V
+
+    def close(self):
+        if self.h:
+            load().lb200_df3c_destroy(self.h)
             self.h = None
 
     def __del__(self):

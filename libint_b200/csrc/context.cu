@@ -437,7 +437,7 @@ int plan_batch(const lb200_context* ctx, const lb200_pairs* bra, const lb200_pai
 // (Cartesian, caller's bra-ket order)
 int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
               long long ntasks, const int2* d_tasks, int screening, double precision,
-              double* d_out) {
+              double* d_out, const ProductTasks* prod) {
   BatchPlan pl;
   int rc = plan_batch(ctx, bra, ket, pl);
   if (rc) return rc;
@@ -447,6 +447,10 @@ int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket
   p.bra = pl.swap ? ket->dev : bra->dev;
   p.ket = pl.swap ? bra->dev : ket->dev;
   p.tasks = d_tasks;
+  if (prod) {   // implicit (bra range) x (ket range) list
+    p.tasks = nullptr;
+    p.prod_nk = (unsigned)prod->nk; p.prod_b0 = prod->b0; p.prod_k0 = prod->k0;
+  }
   p.ntasks_dev = nullptr;
   p.ntasks = (unsigned)ntasks;
   p.swap_tasks = pl.swap ? 1 : 0;
@@ -521,6 +525,39 @@ long long lb200_eri_block_size(const lb200_pairs* bra, const lb200_pairs* ket, i
   auto sz = [&](int l, int pure) { return (pure_out && pure) ? npure(l) : nc(l); };
   return (long long)sz(bra->dev.la, bra->dev.pure_a) * sz(bra->dev.lb, bra->dev.pure_b) *
          sz(ket->dev.la, ket->dev.pure_a) * sz(ket->dev.lb, ket->dev.pure_b);
+}
+
+int lb200_eri_product(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket, int b0, int nb,
+                      int k0, int nk, int screening, double precision, int pure_out, double* out) {
+  if (!ctx || !bra || !ket || !out || b0 < 0 || nb < 0 || k0 < 0 || nk < 0 || b0 + nb > bra->dev.npair ||
+      k0 + nk > ket->dev.npair)
+    return LB200_ERR_INVALID;
+  const long long ntasks = (long long)nb * nk;
+  if (ntasks == 0) return LB200_OK;
+  cudaSetDevice(ctx->device);
+  const int l[4] = {bra->dev.la, bra->dev.lb, ket->dev.la, ket->dev.lb};
+  const int pure[4] = {bra->dev.pure_a, bra->dev.pure_b, ket->dev.pure_a, ket->dev.pure_b};
+  const bool need_tform = pure_out && ((pure[0] && l[0] > 0) || (pure[1] && l[1] > 0) ||
+                                       (pure[2] && l[2] > 0) || (pure[3] && l[3] > 0));
+  ProductTasks pt{b0, nb, k0, nk};
+  if (!need_tform) return run_store(ctx, bra, ket, ntasks, nullptr, screening, precision, out, &pt);
+  // Cartesian integrals into scratch, transformed into the caller's buffer
+  const long long ncart_blk = (long long)nc(l[0]) * nc(l[1]) * nc(l[2]) * nc(l[3]);
+  const size_t need = (size_t)ntasks * ncart_blk * 8;
+  if (ctx->scratch_bytes[1] < need) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_scratch[1]);
+    ctx->d_scratch[1] = nullptr; ctx->scratch_bytes[1] = 0;
+    int rc = check_cuda(ctx, cudaMalloc(&ctx->d_scratch[1], need), "cudaMalloc(scratch)");
+    if (rc) return rc;
+    ctx->scratch_bytes[1] = need;
+  }
+  double* d_cart = static_cast<double*>(ctx->d_scratch[1]);
+  int rc = run_store(ctx, bra, ket, ntasks, nullptr, screening, precision, d_cart, &pt);
+  if (rc) return rc;
+  rc = check_cuda(ctx, launch_pure_transform(ctx, d_cart, out, ntasks, l, pure, ctx->stream), "pure transform");
+  ++ctx->launches;
+  return rc;
 }
 
 int lb200_eri_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,

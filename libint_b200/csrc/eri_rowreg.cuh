@@ -344,7 +344,8 @@ eri_rowreg_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         deg = (double)(1 << ((unsigned)ft.y >> 30));
         ln_prec = __hiloint2double(ft.w, ft.z);
       } else {
-        tk = p.tasks[task];
+        tk = p.prod_nk ? make_int2(p.prod_b0 + (int)(task / p.prod_nk), p.prod_k0 + (int)(task % p.prod_nk))
+                       : p.tasks[task];
       }
       ib = p.swap_tasks ? tk.y : tk.x;
       ik = p.swap_tasks ? tk.x : tk.y;

@@ -154,7 +154,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       r.deg = (double)(1 << ((unsigned)ft.y >> 30));
       r.lnp = __hiloint2double(ft.w, ft.z);
     } else {
-      tk = p.tasks[t];
+      tk = p.prod_nk ? make_int2(p.prod_b0 + (int)(t / p.prod_nk), p.prod_k0 + (int)(t % p.prod_nk)) : p.tasks[t];
     }
     r.t = p.swap_tasks ? make_int2(tk.y, tk.x) : tk;
     return r;

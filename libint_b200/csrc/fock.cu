@@ -19,11 +19,6 @@
 
 #include "internal.h"
 
-namespace lb200 {
-int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
-              long long ntasks, const int2* d_tasks, int screening, double precision,
-              double* d_out);
-}
 
 using namespace lb200;
 
@@ -62,7 +57,7 @@ namespace {
 // sqrt(max |(ab|ab)|) over the functions of each pair of a block (pure where flagged):
 // the quantity both Schwarz set-ups of the reference take from Engine results
 // (hartree-fock++.cc:1283-1286 and :1403-1409)
-int diag_schwarz(lb200_context* ctx, const lb200_pairs* P, std::vector<double>& out) {
+int diag_schwarz_impl(lb200_context* ctx, const lb200_pairs* P, std::vector<double>& out) {
   const long long n = P->dev.npair;
   out.assign(n, 0.0);
   if (n == 0) return LB200_OK;
@@ -317,6 +312,10 @@ __global__ void symmetrize_kernel(const double* __restrict__ F, double* __restri
 
 namespace lb200 {
 
+int diag_schwarz(lb200_context* ctx, const lb200_pairs* P, std::vector<double>& out) {
+  return ::diag_schwarz_impl(ctx, P, out);
+}
+
 int compute_prim_schwarz(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* bs2,
                          int npair, const int* s1, const int* s2, std::vector<double>& out) {
   lb200_basis pb1, pb2;
@@ -333,7 +332,7 @@ int compute_prim_schwarz(lb200_context* ctx, const lb200_basis* bs1, const lb200
   int rc = build_pairs(ctx, &pb1, &pb2, (int)q1.size(), q1.data(), q2.data(), kScreenOriginal,
                        std::numeric_limits<double>::lowest(), nullptr, nullptr, &P);
   if (rc) return rc;
-  rc = diag_schwarz(ctx, P, out);
+  rc = diag_schwarz_impl(ctx, P, out);
   lb200_pairs_destroy(P);
   return rc;
 }
@@ -397,7 +396,7 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
     rc = build_pairs(ctx, obs, obs, n, a.data(), b.data(), kScreenOriginal,
                      std::numeric_limits<double>::lowest(), nullptr, nullptr, &all);
     std::vector<double> ksh;
-    if (!rc) rc = diag_schwarz(ctx, all, ksh);
+    if (!rc) rc = diag_schwarz_impl(ctx, all, ksh);
     lb200_pairs_destroy(all);
     if (rc) break;
     // sort the class by Schwarz bound, descending (stable for reproducibility)

@@ -60,6 +60,13 @@ int order_key(int la, int lb);
 cudaError_t launch_eri(int la, int lb, int lc, int ld, const EriParams& p, const RowInfo* rows,
                        int mode, int num_sms, cudaStream_t stream);
 
+// implicit task list of run_store: every (bra pair b0 + i, ket pair k0 + j), i < nb, j < nk, j fastest
+struct ProductTasks { int b0, nb, k0, nk; };
+// store-mode launch for device-resident tasks (explicit list, or `prod`) into a device buffer (Cartesian)
+int run_store(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket, long long ntasks,
+              const int2* d_tasks, int screening, double precision, double* d_out,
+              const ProductTasks* prod = nullptr);
+
 // generic cart -> pure transform of a batch of shell sets (transform.cu)
 cudaError_t launch_pure_transform(const lb200_context* ctx, const double* in, double* out,
                                   long long ntasks, const int l[4], const int pure[4],

@@ -72,7 +72,11 @@ struct PrereqRec {
 
 struct EriParams {
   PairBlock bra, ket;        // kernel-internal orientation: bra = "lane side"
-  const int2* tasks;         // (bra pair, ket pair) indices (store modes)
+  const int2* tasks;         // (bra pair, ket pair) indices (store modes); null with prod_nk > 0
+  // implicit Cartesian-product task list (store modes): task t = (prod_b0 + t / prod_nk, prod_k0 + t % prod_nk)
+  // in the CALLER's bra/ket orientation (swap_tasks applies afterwards); no task array is read
+  unsigned prod_nk;
+  int prod_b0, prod_k0;
   // Fock mode: one 16-byte record per surviving quartet, written by the screening kernel:
   // x = bra pair, y = ket pair | degeneracy code << 30 (deg = 1 << code, hartree-fock++.cc:1683-1687),
   // (z, w) = ln of the engine precision of this quartet (hartree-fock++.cc:1693-1695) as a double

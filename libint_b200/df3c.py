@@ -63,6 +63,9 @@ class ThreeCenter:
         view)` sees each finished chunk.  Returns the number of shell triplets computed."""
         import torch
         dev = out.device
+        # the kernels run on the context's stream: make it torch's current one, so that `out` is not
+        # overwritten while a sink on the torch stream still reads the previous chunk
+        self.ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         total = 0
         for kb, kk in self.blocks():
             cls = (kb[0], kk[0], kk[1])
@@ -73,13 +76,22 @@ class ThreeCenter:
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record(torch.cuda.current_stream(dev))
-            for t0 in range(0, n, per):
-                m = min(per, n - t0)
-                t = torch.arange(t0, t0 + m, device=dev, dtype=torch.int64)
-                tasks = torch.stack((t // ket.npair, t % ket.npair), dim=1).to(torch.int32).contiguous()
-                capi.eri_batch(self.ctx, bra, ket, tasks, out=out[:m * blk])
+            # whole bra rows per launch: an implicit (DF shells) x (orbital pairs) product, no task list
+            rows = max(1, per // ket.npair)
+            for b0 in range(0, bra.npair, rows):
+                nb = min(rows, bra.npair - b0)
+                m = nb * ket.npair
+                if m * blk > out.numel():   # one row does not fit: split it over ket ranges
+                    kper = max(1, out.numel() // blk)
+                    for k0 in range(0, ket.npair, kper):
+                        nk = min(kper, ket.npair - k0)
+                        capi.eri_product(self.ctx, bra, ket, b0, 1, k0, nk, out)
+                        if sink is not None:
+                            sink((kb, kk), b0 * ket.npair + k0, nk, out[:nk * blk].view(nk, blk))
+                    continue
+                capi.eri_product(self.ctx, bra, ket, b0, nb, 0, ket.npair, out)
                 if sink is not None:
-                    sink((kb, kk), t0, m, out[:m * blk].view(m, blk))
+                    sink((kb, kk), b0 * ket.npair, m, out[:m * blk].view(m, blk))
             if events is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record(torch.cuda.current_stream(dev))
