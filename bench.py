@@ -386,7 +386,7 @@ def main():
     df3c = None
     if not args.no_df3c:
         try:
-            df3c = run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world)
+            df3c = run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world, rank, hbm_peak)
         except capi.Lb200Error as e:
             df3c = {"error": str(e)}
 
@@ -464,9 +464,12 @@ def sweep_parity(ctx, work, npairs, per_class=20000):
             "classes": len(per), "seconds": time.perf_counter() - t0, "per_class": per}
 
 
-def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world):
-    """every (P|mu nu) shell triplet of an all-trans alkane once (replicated per rank: the tensor
-    shards by DF shell with no collective, SURVEY 8e -- here each rank sweeps the whole list)."""
+def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world, rank=0, hbm_peak=6469.9):
+    """configs[3]: every (P|mu nu) shell triplet of an all-trans alkane once, as implicit (DF shell) x (orbital
+    pair) products per class (lb200_eri_product, Cartesian, materialised in HBM).  Sharded by DF shell over the
+    ranks with no collective: each rank sweeps its contiguous share of every bra block.  Beside
+    it: the reference Engine's xs_xx loop on the host cores (bounded sample), the HBM roofline of the write,
+    and the density-fitted Fock build that consumes the integrals (libint_b200.dfjk)."""
     import torch
     from libint_b200.basis import BasisSet, alkane
     from libint_b200.df3c import ThreeCenter
@@ -476,32 +479,83 @@ def run_df3c(args, ctx, dev, stream, out, barrier, max_over_ranks, world):
     tc = ThreeCenter(ctx, obs, dfbs)
     setup_s = time.perf_counter() - t0
     with torch.cuda.stream(stream):
-        tc.sweep(out)
+        tc.sweep(out, rank=rank, nranks=world)
         barrier()
         ev = []
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        n = tc.sweep(out, events=ev)
+        n_mine = tc.sweep(out, events=ev, rank=rank, nranks=world)
         e1.record(stream)
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    nints = sum(nn * blk for _, nn, blk, _, _ in ev)
+    n = tc.ntriplets()
+    nints_mine = sum(nn * blk for _, nn, blk, _, _ in ev)
     agg = {}
     for c, nn, blk, a, b in ev:   # merge the contraction buckets of a class
-        e = agg.setdefault(c, [0, 0.0])
+        e = agg.setdefault(c, [0, 0.0, blk])
         e[0] += nn
         e[1] += a.elapsed_time(b)
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]
-    return {"workload": "C%dH%d (P|mu nu), obs def2-tzvp (%d shells, %d bf), dfbs def2-tzvp-jk (%d shells, %d bf, "
-                        "max l %d), %d significant orbital pairs" % (args.df3c_carbons, 2 * args.df3c_carbons + 2,
-                                                                      len(obs), obs.nbf, len(dfbs), dfbs.nbf,
-                                                                      dfbs.max_l, tc.npairs),
-            "shell_triplets": n, "classes": len(tc.classes()), "launch_groups": len(tc.blocks()), "seconds": ms * 1e-3,
-            "triplets_per_s": n / (ms * 1e-3), "cartesian_integrals": nints,
-            "hbm_write_gbs": nints * 8 / (ms * 1e-3) / 1e9, "setup_seconds": setup_s,
-            "slowest_classes": [{"class": "(%d s|%d %d)" % c, "triplets": nn,
-                                 "ns_per_triplet": 1e6 * t / nn} for c, (nn, t) in top]}
+    dom_c, (dom_n, dom_ms, dom_blk) = top[0]
+    res = {"workload": "C%dH%d (P|mu nu), obs def2-tzvp (%d shells, %d bf), dfbs def2-tzvp-jk (%d shells, %d bf, "
+                       "max l %d), %d significant orbital pairs" % (args.df3c_carbons, 2 * args.df3c_carbons + 2,
+                                                                     len(obs), obs.nbf, len(dfbs), dfbs.nbf,
+                                                                     dfbs.max_l, tc.npairs),
+           "shell_triplets": n, "classes": len(tc.classes()), "launch_groups": len(tc.blocks()), "seconds": ms * 1e-3,
+           "triplets_per_s": n / (ms * 1e-3), "n_gpus": world, "scaling": "strong",
+           "sharding": "by DF shell (bra rows of every class block), no collective",
+           "cartesian_integrals_this_rank": nints_mine,
+           "hbm_write_gbs": nints_mine * 8 / (ms * 1e-3) / 1e9, "setup_seconds": setup_s,
+           "roofline": {"bound": "hbm", "kernel": "store-mode class kernel (%d s|%d %d)" % dom_c,
+                        "achieved": dom_n * dom_blk * 8 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "frac": dom_n * dom_blk * 8 / (dom_ms * 1e-3) / 1e9 / hbm_peak if dom_ms > 0 else 0.0,
+                        "whole_sweep_frac": nints_mine * 8 / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "algorithmic bytes = 8 x Cartesian integrals written; the sweep is 100+ small "
+                                "launches, the dominant class is timed with CUDA events around its launches"},
+           "slowest_classes": [{"class": "(%d s|%d %d)" % c, "triplets": nn,
+                                "ns_per_triplet": 1e6 * t / nn} for c, (nn, t, _) in top]}
+    if rank == 0 and not args.no_cpu_baseline:
+        # the reference's DF set-up loop on the host cores: a bounded random sample of the same triplets
+        from oracle import pyoracle as po
+        ncores = os.cpu_count() or 1
+        rng = np.random.default_rng(11)
+        ns = 4000000
+        k = rng.integers(0, tc.npairs, ns)
+        t3 = np.stack([rng.integers(0, len(dfbs), ns), tc.pair_a[k], tc.pair_b[k]], axis=1).astype(np.int32)
+        sec, _ = po.time_triplets(po.Shells(*dfbs.flat(), raw=False), po.Shells(*obs.flat(), raw=False), t3, ncores)
+        res["cpu_baseline"] = {"value": ns / sec, "unit": "shell triplets/s", "cores": ncores, "kind": "port",
+                               "sample": "%d random (DF shell, significant orbital pair) triplets of the same workload, "
+                                         "reference Engine xs_xx, %.1f s" % (ns, sec)}
+    # the consumer: density-fitted G = 2J - K with streamed slabs (one rank; needs the memory of W)
+    if rank == 0 and args.df3c_carbons >= 8:
+        try:
+            from libint_b200.dfjk import DFFockBuilder
+            with torch.cuda.stream(stream):
+                t0 = time.perf_counter()
+                fb = DFFockBuilder(obs, dfbs, ctx=ctx, slab_bytes=8 << 30, threshold=0.0)
+                torch.cuda.synchronize(dev)
+                dsetup = time.perf_counter() - t0
+                nocc = sum(a.atomic_number for a in atoms) // 2
+                C = torch.linalg.qr(torch.randn((obs.nbf, nocc), dtype=torch.float64, device=dev,
+                                                generator=torch.Generator(device=dev).manual_seed(3)))[0]
+                fb(C)
+                torch.cuda.synchronize(dev)
+                d0 = torch.cuda.Event(enable_timing=True)
+                d1 = torch.cuda.Event(enable_timing=True)
+                d0.record(stream)
+                G = fb(C)
+                d1.record(stream)
+                torch.cuda.synchronize(dev)
+            res["dfjk"] = {"workload": "density-fitted G = 2J - K, nocc %d, ndf %d, %d slabs x 2 sweeps" % (nocc, dfbs.nbf, len(fb.slabs)),
+                           "seconds": d0.elapsed_time(d1) * 1e-3, "setup_seconds_metric_cholesky": dsetup,
+                           "checksum": float(G.abs().sum().item()), "symmetric_err": float((G - G.T).abs().max().item())}
+            del fb, G, C
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001 -- report, do not lose the bench line
+            res["dfjk"] = {"error": repr(e)[:300]}
+    return res
 
 
 def fock_roofline(f, fp64_peak, build_seconds, pure_basis=True):

@@ -146,6 +146,10 @@ int lb200_eri_prereq_batch(lb200_context* ctx, int la, int lb, int lc, int ld, l
  *      SchwarzInf primitive-pair data (:1383-1431) on the GPU. */
 int lb200_significant_pairs(const lb200_basis* bs, double threshold, int* s1, int* s2,
                             long long cap, long long* count);
+/* the same list evaluated on the GPU (one thread per shell pair); cap >= nshell(nshell+1)/2 returns the
+ * whole list in one call */
+int lb200_significant_pairs_device(lb200_context* ctx, const lb200_basis* bs, double threshold, int* s1,
+                                   int* s2, long long cap, long long* count);
 int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npair, const int* s1,
                       const int* s2, lb200_fock** out);
 int lb200_fock_destroy(lb200_fock* f);

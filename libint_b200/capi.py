@@ -58,6 +58,8 @@ SIGNATURES = {
     "lb200_eri_class_supported": (C.c_int, [C.c_int] * 4),
     "lb200_significant_pairs": (C.c_int, [vp, C.c_double, ip, ip, C.c_longlong,
                                           C.POINTER(C.c_longlong)]),
+    "lb200_significant_pairs_device": (C.c_int, [vp, vp, C.c_double, ip, ip, C.c_longlong,
+                                                 C.POINTER(C.c_longlong)]),
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
@@ -276,7 +278,17 @@ def eri_batch(ctx, bra, ket, tasks, out=None, screening=SCREEN_ORIGINAL, precisi
     return out
 
 
-def significant_pairs(bs, threshold=1e-12):
+def significant_pairs(bs, threshold=1e-12, device=True):
+    """obs_shellpair_list of the reference (hartree-fock++.cc:1305-1381) as two int32 arrays (s1 >= s2).
+    device=True: evaluated by a GPU kernel on the basis' context; False: the serial host loop."""
+    if device and getattr(bs, "ctx", None) is not None:
+        cap = bs.nshell * (bs.nshell + 1) // 2
+        s1 = np.zeros(cap, dtype=np.int32)
+        s2 = np.zeros(cap, dtype=np.int32)
+        cnt = C.c_longlong(0)
+        bs.ctx.check(load().lb200_significant_pairs_device(bs.ctx.h, bs.h, float(threshold), _i(s1), _i(s2), cap,
+                                                           C.byref(cnt)), "significant_pairs_device")
+        return s1[:cnt.value].copy(), s2[:cnt.value].copy()
     cnt = C.c_longlong(0)
     load().lb200_significant_pairs(bs.h, float(threshold), None, None, 0, C.byref(cnt))
     s1 = np.zeros(cnt.value, dtype=np.int32)

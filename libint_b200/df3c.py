@@ -44,6 +44,7 @@ class ThreeCenter:
             idx = np.nonzero((ldf == key[0]) & (cdf == key[1]))[0].astype(np.int32)
             self.bras[key] = capi.Pairs(ctx, self.Bdf, self.unit, idx, np.zeros_like(idx))
         self.npairs = int(len(a))
+        self.pair_a, self.pair_b = a.astype(np.int32), b.astype(np.int32)   # first shell = higher AM
 
     def blocks(self):
         """(bra key, ket key) of every launch group; bra key = (L, contracted), ket key =
@@ -57,10 +58,12 @@ class ThreeCenter:
     def ntriplets(self):
         return sum(self.bras[kb].npair * self.kets[kk].npair for kb, kk in self.blocks())
 
-    def sweep(self, out, chunk_bytes=1 << 30, sink=None, events=None):
+    def sweep(self, out, chunk_bytes=1 << 30, sink=None, events=None, rank=0, nranks=1):
         """Every (P|mu nu) shell triplet once, class by class, Cartesian, into the device
         buffer `out` (torch CUDA float64, reused chunk after chunk).  `sink((bra key, ket key), t0, n,
-        view)` sees each finished chunk.  Returns the number of shell triplets computed."""
+        view)` sees each finished chunk.  With nranks > 1 this rank takes its contiguous share of the DF
+        shells of every bra block (the tensor shards by P, no collective).  Returns the number of shell
+        triplets this rank computed."""
         import torch
         dev = out.device
         # the kernels run on the context's stream: make it torch's current one, so that `out` is not
@@ -71,15 +74,16 @@ class ThreeCenter:
             cls = (kb[0], kk[0], kk[1])
             bra, ket = self.bras[kb], self.kets[kk]
             blk = capi.eri_block_size(bra, ket)
-            n = bra.npair * ket.npair
-            per = max(1, min(n, min(out.numel(), chunk_bytes // 8) // blk))
+            r_lo, r_hi = bra.npair * rank // nranks, bra.npair * (rank + 1) // nranks
+            n = (r_hi - r_lo) * ket.npair
+            per = max(1, min(max(n, 1), min(out.numel(), chunk_bytes // 8) // blk))
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record(torch.cuda.current_stream(dev))
             # whole bra rows per launch: an implicit (DF shells) x (orbital pairs) product, no task list
             rows = max(1, per // ket.npair)
-            for b0 in range(0, bra.npair, rows):
-                nb = min(rows, bra.npair - b0)
+            for b0 in range(r_lo, r_hi, rows):
+                nb = min(rows, r_hi - b0)
                 m = nb * ket.npair
                 if m * blk > out.numel():   # one row does not fit: split it over ket ranges
                     kper = max(1, out.numel() // blk)

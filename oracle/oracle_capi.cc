@@ -520,6 +520,47 @@ double lbo_time_quartets(int nshell, const int* l, const int* pure, const int* n
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Time the reference Engine (xs_xx: bra1, unit shell, ket1, ket2) on a list of shell triplets, the
+// DF set-up loop of hartree-fock++.cc:2215-2262 (one Engine per thread, round-robin).  t3 = nt x
+// {DF shell in table 1, orbital shell, orbital shell in table 2}.
+double lbo_time_triplets(int ns1, const int* l1, const int* pure1, const int* nprim1, const double* O1,
+                         const double* alpha1, const double* coeff1, int ns2, const int* l2, const int* pure2,
+                         const int* nprim2, const double* O2, const double* alpha2, const double* coeff2,
+                         long nt, const int* t3, int nthreads, double* sum) {
+  lbo_init();
+  auto dfs = make_shells(ns1, l1, pure1, nprim1, O1, alpha1, coeff1, 0);
+  auto obs = make_shells(ns2, l2, pure2, nprim2, O2, alpha2, coeff2, 0);
+  int max_nprim = 0, max_l = 0;
+  for (auto* v : {&dfs, &obs})
+    for (auto& s : *v) {
+      max_nprim = std::max<int>(max_nprim, s.nprim());
+      max_l = std::max<int>(max_l, s.contr[0].l);
+    }
+  const int nthr = std::max(1, nthreads);
+  std::vector<Engine> engines(nthr);
+  engines[0] = Engine(Operator::coulomb, max_nprim, max_l, 0);
+  engines[0].set(BraKet::xs_xx);
+  for (int i = 1; i < nthr; ++i) engines[i] = engines[0];
+  std::vector<double> sums(nthr, 0.0);
+  const auto& unit = Shell::unit();
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  parallel_do(nthr, [&](int tid) {
+    auto& e = engines[tid];
+    const auto& buf = e.results();
+    double s = 0;
+    for (long q = tid; q < nt; q += nthr) {
+      e.compute2<Operator::coulomb, BraKet::xs_xx, 0>(dfs[t3[3 * q]], unit, obs[t3[3 * q + 1]], obs[t3[3 * q + 2]]);
+      if (buf[0]) s += buf[0][0];
+    }
+    sums[tid] = s;
+  });
+  const auto t1 = std::chrono::high_resolution_clock::now();
+  double s = 0;
+  for (auto v : sums) s += v;
+  if (sum) *sum = s;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // A list of shell quartets of one class through the reference Engine (xx_xx), results
 // (row-major n1*n2*n3*n4, pure where flagged) written to out[q * blk ...]; a set the Engine
 // screens out entirely (results()[0] == nullptr) gives zeros.  Returns blk, < 0 on error.

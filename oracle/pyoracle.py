@@ -98,6 +98,9 @@ def lib(fast=False, b200=False):
         L.lbo_time_quartets.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_long, ip,
                                         C.c_int, C.c_int, dp]
         L.lbo_time_quartets.restype = C.c_double
+        L.lbo_time_triplets.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, ip, ip, ip, dp, dp, dp,
+                                        C.c_long, ip, C.c_int, dp]
+        L.lbo_time_triplets.restype = C.c_double
         L.lbo_compute_batch.argtypes = [C.c_int, ip, ip, ip, dp, dp, dp, C.c_int, C.c_long, ip,
                                         C.c_int, C.c_double, dp]
         L.lbo_compute_batch.restype = C.c_long
@@ -285,6 +288,16 @@ def time_quartets(shells, quartets, nthreads=1, use_pairs=True, fast=True):
     t = lib(fast).lbo_time_quartets(len(shells), *shells.args(), len(q), _i(q), int(nthreads),
                                     int(bool(use_pairs)), C.byref(s))
     return t, s.value
+
+
+def time_triplets(dfshells, obsshells, triplets, nthreads=1, fast=True):
+    """wall seconds of Engine(xs_xx).compute2(df[P], unit, obs[a], obs[b]) over the triplet list."""
+    t = np.ascontiguousarray(triplets, dtype=np.int32).reshape(-1, 3)
+    s = C.c_double(0)
+    a1, a2 = dfshells.args()[:-1], obsshells.args()[:-1]
+    sec = lib(fast).lbo_time_triplets(len(dfshells), *a1, len(obsshells), *a2, len(t), _i(t), int(nthreads),
+                                      C.byref(s))
+    return sec, s.value
 
 
 def compute_batch(shells, quartets, nthreads=1, precision=0.0):

@@ -192,3 +192,20 @@ def test_fock_pure_p_shell_and_mixed(ctx, oracle):
     bs[first_p].pure = True
     bs._refresh()
     _purity_case(ctx, oracle, bs, "G (H2O)2/cc-pVDZ mixed purity")
+
+
+def test_significant_pairs_device_matches_host(ctx):
+    """compute_shellpairs (hartree-fock++.cc:1305-1381) on the GPU == the host loop, for a cluster large
+    enough that most pairs are dropped, Cartesian and pure shells."""
+    from libint_b200 import capi
+    from libint_b200.basis import BasisSet, water_cluster
+    for name, pure in (("def2-tzvp", None), ("cc-pvdz", False)):
+        bs = BasisSet(name, water_cluster(3, 2, 2))
+        if pure is not None:
+            bs.set_pure(pure)
+        B = capi.Basis(ctx, *bs.flat())
+        for thr in (1e-12, 1e-8):
+            d1, d2 = capi.significant_pairs(B, thr, device=True)
+            h1, h2 = capi.significant_pairs(B, thr, device=False)
+            assert len(d1) < B.nshell * (B.nshell + 1) // 2
+            assert np.array_equal(d1, h1) and np.array_equal(d2, h2)
