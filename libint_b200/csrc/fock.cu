@@ -42,8 +42,15 @@ struct lb200_fock {
   double* d_scalar = nullptr;
   int* d_shell2bf = nullptr;
   int* d_shellsize = nullptr;
-  int4* d_tasks = nullptr;   // task records (types.cuh: EriParams::ftasks)
-  unsigned* d_count = nullptr;
+  // Class pairs are issued round-robin on a few side streams, each with its own task buffer and
+  // counters: the tail of one class kernel (a few long quartets on a few SMs) overlaps the screening
+  // and the start of the next pair instead of idling the GPU ~1200 times per build.
+  static constexpr int kMaxStreams = 8;
+  int nstreams = 0;
+  cudaStream_t streams[kMaxStreams] = {};
+  cudaEvent_t ev_ready = nullptr, ev_done[kMaxStreams] = {};
+  int4* d_tasks[kMaxStreams] = {};   // task records (types.cuh: EriParams::ftasks)
+  unsigned* d_count[kMaxStreams] = {};   // [0] task count, [1] dynamic-scheduling cursor of the class kernel
   long long task_cap = 0;
   // per (bra class, ket class) timings of the last build, filled when profiling is on
   bool profile = false;
@@ -432,7 +439,19 @@ int lb200_fock_create(lb200_context* ctx, const lb200_basis* obs, long long npai
   cudaMalloc(&f->d_shellsize, ns * sizeof(int));
   cudaMalloc(&f->d_Dnorm, (size_t)ns * ns * 8);
   cudaMalloc(&f->d_scalar, 8);
-  cudaMalloc(&f->d_count, 8);   // [0] task count, [1] dynamic-scheduling cursor of the class kernel
+  {
+    int nsr = 4;
+    if (const char* e = std::getenv("LB200_FOCK_STREAMS")) nsr = std::atoi(e);
+    f->nstreams = std::max(1, std::min(nsr, (int)lb200_fock::kMaxStreams));
+    cudaEventCreateWithFlags(&f->ev_ready, cudaEventDisableTiming);
+    for (int k = 0; k < f->nstreams; ++k) {
+      cudaMalloc(&f->d_count[k], 8);
+      if (k > 0) {   // slot 0 is the context's own stream
+        cudaStreamCreateWithFlags(&f->streams[k], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&f->ev_done[k], cudaEventDisableTiming);
+      }
+    }
+  }
   cudaMemcpy(f->d_shell2bf, obs->shell2bf.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(f->d_shellsize, ssz.data(), ns * sizeof(int), cudaMemcpyHostToDevice);
   rc = check_cuda(ctx, cudaGetLastError(), "fock_create");
@@ -446,7 +465,13 @@ int lb200_fock_destroy(lb200_fock* f) {
   cudaSetDevice(f->ctx->device);
   for (auto& c : f->classes) { lb200_pairs_destroy(c.pairs); cudaFree(c.d_dn); }
   cudaFree(f->d_D); cudaFree(f->d_F); cudaFree(f->d_Dnorm); cudaFree(f->d_scalar);
-  cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize); cudaFree(f->d_tasks); cudaFree(f->d_count);
+  cudaFree(f->d_shell2bf); cudaFree(f->d_shellsize);
+  for (int k = 0; k < lb200_fock::kMaxStreams; ++k) {
+    cudaFree(f->d_tasks[k]); cudaFree(f->d_count[k]);
+    if (k > 0 && f->streams[k]) cudaStreamDestroy(f->streams[k]);   // slot 0 is the context's stream
+    if (f->ev_done[k]) cudaEventDestroy(f->ev_done[k]);
+  }
+  if (f->ev_ready) cudaEventDestroy(f->ev_ready);
   cudaFree(f->d_primcount);
   delete f;
   return LB200_OK;
@@ -524,20 +549,31 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
   if ((rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock: D norms"))) return rc;
   const double fock_precision = precision;
   const double needed_engine_precision = fock_precision / Dmax;  // hartree-fock++.cc:1588
-  // task buffer
-  const long long cap = 1ll << 24;
-  if (f->task_cap < cap) {
-    cudaFree(f->d_tasks);
-    if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks, cap * sizeof(int4)), "cudaMalloc(tasks)")))
-      return rc;
-    f->task_cap = cap;
-  }
-  const double thr_num = fock_precision / Dmax * (1.0 - 1e-12);
-  double nquartets = 0, ncand = 0;
-  std::vector<unsigned> jmax;
   // LB200_FOCK_PROFILE=1: per class-pair device time (one sync per launch; diagnostics only)
   const bool env_profile = stats && std::getenv("LB200_FOCK_PROFILE");
   const bool profile = env_profile || f->profile;
+  // streams in use: one (the context's) when per-launch accounting is wanted, else all of them
+  const int NS = (profile || stats) ? 1 : f->nstreams;
+  // task buffers
+  const long long cap = 1ll << 24;
+  if (f->task_cap < cap) {
+    for (int k = 0; k < f->nstreams; ++k) {
+      cudaFree(f->d_tasks[k]);
+      f->d_tasks[k] = nullptr;
+      if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks[k], cap * sizeof(int4)), "cudaMalloc(tasks)")))
+        return rc;
+    }
+    f->task_cap = cap;
+  }
+  f->streams[0] = st;
+  if (NS > 1) {   // side streams start after the density norms are on the device
+    cudaEventRecord(f->ev_ready, st);
+    for (int k = 1; k < NS; ++k) cudaStreamWaitEvent(f->streams[k], f->ev_ready, 0);
+  }
+  int next_stream = 0;
+  const double thr_num = fock_precision / Dmax * (1.0 - 1e-12);
+  double nquartets = 0, ncand = 0;
+  std::vector<unsigned> jmax;
   using Prof = lb200_fock::ProfRow;
   std::vector<Prof>& prof = f->prof;
   prof.clear();
@@ -581,6 +617,11 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
         if (sum > cap) return set_error(ctx, LB200_ERR_NOMEM, "task buffer too small for one row");
         if (sum > 0) {
           ncand += (double)sum;
+          const int sidx = next_stream;
+          next_stream = (next_stream + 1) % NS;
+          cudaStream_t st = f->streams[sidx];   // shadows the context's stream inside this launch pair
+          int4* const d_tasks = f->d_tasks[sidx];
+          unsigned* const d_count = f->d_count[sidx];
           ScreenParams sp{};
           sp.bra = B.pairs->dev; sp.ket = Kt.pairs->dev;
           sp.same_class = (X == Y);
@@ -591,8 +632,8 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
           sp.ln_needed_engine_precision = std::log(needed_engine_precision);
           sp.rank = rank; sp.nranks = nranks;
-          sp.tasks = f->d_tasks; sp.count = f->d_count; sp.cap = (unsigned)cap;
-          cudaMemsetAsync(f->d_count, 0, 8, st);
+          sp.tasks = d_tasks; sp.count = d_count; sp.cap = (unsigned)cap;
+          cudaMemsetAsync(d_count, 0, 8, st);
           const int threads = 128;
           const size_t row_bytes = 2 * (size_t)ns * sizeof(double);
           sp.stage_rows = row_bytes <= (size_t)96 * 1024;
@@ -602,8 +643,8 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           ++ctx->launches;
           EriParams p{};
           p.bra = B.pairs->dev; p.ket = Kt.pairs->dev;
-          p.tasks = nullptr; p.ftasks = f->d_tasks; p.ntasks_dev = f->d_count; p.ntasks = 0; p.swap_tasks = 0;
-          p.work_counter = f->d_count + 1;
+          p.tasks = nullptr; p.ftasks = d_tasks; p.ntasks_dev = d_count; p.ntasks = 0; p.swap_tasks = 0;
+          p.work_counter = d_count + 1;
           // uncontracted x uncontracted bucket: the pipelined kernel (LB200_NO_PRIM_KERNEL=1: A/B)
           static const bool no_prim = std::getenv("LB200_NO_PRIM_KERNEL") != nullptr;
           p.uncontracted = (!no_prim && p.bra.max_nprim <= 1 && p.ket.max_nprim <= 1) ? 1 : 0;
@@ -634,7 +675,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
             cudaEventElapsedTime(&ms, pe0, pe1);
             unsigned c = 0;
             unsigned long long np = 0, npc[kPrimCounters];
-            cudaMemcpy(&c, f->d_count, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&c, d_count, 4, cudaMemcpyDeviceToHost);
             cudaMemcpy(npc, f->d_primcount, 8 * kPrimCounters, cudaMemcpyDeviceToHost);
             for (int k = 0; k < kPrimCounters; ++k) np += npc[k];
             bool found = false;
@@ -648,7 +689,7 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
           }
           if (stats) {  // optional accounting costs a sync per chunk
             unsigned c = 0;
-            cudaMemcpyAsync(&c, f->d_count, 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&c, d_count, 4, cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);
             nquartets += c;
           }
@@ -656,6 +697,12 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
         row = r1;
       }
     }
+  if (NS > 1) {   // the context's stream continues after every side stream has drained
+    for (int k = 1; k < NS; ++k) {
+      cudaEventRecord(f->ev_done[k], f->streams[k]);
+      cudaStreamWaitEvent(st, f->ev_done[k], 0);
+    }
+  }
   if (rc) return rc;
   if (profile) {
     std::sort(prof.begin(), prof.end(), [](const Prof& a, const Prof& b) { return a.ms > b.ms; });
