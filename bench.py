@@ -328,7 +328,8 @@ def main():
     roofline.update(hbm_side if hbm_bound else fp64_side)
     roofline.update({"traffic": traffic, "algorithmic_bytes": float(bytes_q * chunk),
                      "flops_per_byte": intensity, "machine_balance_flops_per_byte": balance,
-                     "launch_ms": d["ms"] / nchunks, "share_of_step": d["ms"] / ms_step,
+                     "launch_ms": d["ms"] * chunk / nq,   # CUDA-event time of the class scaled to one full-size launch
+                     "share_of_step": d["ms"] / ms_step,
                      "fp64": fp64_side, "hbm": hbm_side})
 
     # ---- e2e: host buffers through the C ABI (pinned tasks in, integrals out) ----------

@@ -92,8 +92,10 @@ int lb200_basis_shell2bf(const lb200_basis* bs, int* out);
  *      All pairs of one call must belong to one class (l(s1) >= l(s2), same l's and purity).
  *      screening: ORIGINAL / CONSERVATIVE use ln_prec as in shell.h:1162-1232;
  *      SCHWARZ / SCHWARZ_INF need prim_schwarz (one factor per primitive pair, ordered
- *      [pair][p1][p2], = schwarz_factor_evaluator of hartree-fock++.cc:1390-1412) or NULL to
- *      have the library compute them on the GPU. */
+ *      [pair][p1][p2], = schwarz_factor_evaluator of hartree-fock++.cc:1390-1412); for SCHWARZ_INF
+ *      NULL makes the library compute them on the GPU (sqrt of max |(ab|ab)| per primitive pair);
+ *      SCHWARZ (Frobenius norm) with NULL is rejected with LB200_ERR_INVALID.
+ *      All pairs of one block share one kind of second shell (ordinary or Shell::unit()). */
 int lb200_pairs_create(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* bs2,
                        int npair, const int* s1, const int* s2, int screening, double ln_prec,
                        const double* prim_schwarz, lb200_pairs** out);

@@ -258,6 +258,12 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     return set_error(ctx, LB200_ERR_INVALID, "invalid screening method");
   const bool schwarz = screening == kScreenSchwarz || screening == kScreenSchwarzInf;
   std::vector<double> computed;
+  // the library's own evaluator is the SchwarzInf one (sqrt of the largest |(ab|ab)| of the primitive
+  // pair, hartree-fock++.cc:1403-1409); ScreeningMethod::Schwarz wants the Frobenius norm, which only a
+  // caller-supplied table can provide
+  if (screening == kScreenSchwarz && !prim_schwarz && npair > 0)
+    return set_error(ctx, LB200_ERR_INVALID,
+                     "LB200_SCREEN_SCHWARZ needs prim_schwarz (the built-in evaluator is SchwarzInf)");
   if (schwarz && !prim_schwarz && npair > 0) {
     int rc = compute_prim_schwarz(ctx, bs1, bs2, npair, s1, s2, computed);
     if (rc) return rc;

@@ -95,10 +95,19 @@ class Engine:
         b2 = basis_handle(self.ctx, [second])
         # ShellPair::init with the engine's own ln_precision (engine.impl.h:1258-1276)
         lnp = np.log(self.precision) if self.precision > 0 else -np.inf
+        scr = self._checked_screening()
+        return capi.Pairs(self.ctx, b1, b2, [0], [0], int(scr), lnp), swapped, (b1, b2)
+
+    def _checked_screening(self):
+        """The Schwarz methods need ShellPairs built with a schwarz_factor_evaluator (shell.h:1259-1328);
+        Engine::compute2 without precomputed pairs asserts on them in the reference
+        (engine.impl.h:1259-1276 -> ShellPair::init).  This mirror has no per-call evaluator either:
+        refuse instead of silently screening differently."""
         scr = self.screening_method
         if scr in (ScreeningMethod.Schwarz, ScreeningMethod.SchwarzInf):
-            scr = ScreeningMethod.Original  # Schwarz factors need a caller-supplied evaluator
-        return capi.Pairs(self.ctx, b1, b2, [0], [0], int(scr), lnp), swapped, (b1, b2)
+            raise ValueError("Engine.compute: ScreeningMethod.%s needs precomputed shell pairs "
+                             "(use capi.Pairs(..., screening=SCREEN_SCHWARZ_INF) / FockBuilder)" % scr.name)
+        return scr
 
     def compute(self, *shells):
         """compute2<coulomb, braket, 0>; returns a flat array or None when screened out."""
@@ -118,9 +127,7 @@ class Engine:
             s2 = s4 = Shell.unit()
         bra, sw_b, keep1 = self._pairs(s1, s2)
         ket, sw_k, keep2 = self._pairs(s3, s4)
-        scr = self.screening_method
-        if scr in (ScreeningMethod.Schwarz, ScreeningMethod.SchwarzInf):
-            scr = ScreeningMethod.Original
+        scr = self._checked_screening()
         out = capi.eri_batch(self.ctx, bra, ket, np.array([[0, 0]], dtype=np.int32),
                              screening=int(scr), precision=self.precision, pure_out=True)[0]
         if bra.nprimpair == 0 or ket.nprimpair == 0:
