@@ -600,7 +600,7 @@ def fock_roofline(f, fp64_peak, build_seconds, pure_basis=True):
             "frac_with_digestion": (tot_flops + tot_dig) / build_seconds / 1e12 / fp64_peak,
             "note": "achieved/frac: this rank's model flops over the timed (unprofiled) build; per-class rows from "
                     "a separate profiled build (one stream sync per launch)",
-            "classes": len(out), "top_classes": out[:12]}
+            "classes": len(out), "top_classes": out[:12], "all_classes": out}
 
 
 def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_, fp64_peak=None,

@@ -178,6 +178,13 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
 int lb200_eri_product(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket, int b0, int nb,
                       int k0, int nk, int screening, double precision, int pure_out, double* out_device);
 
+/* ---- one-body integrals on the GPU: overlap S, kinetic T, nuclear attraction V of a basis, the three
+ *      compute_1body_ints<Operator::overlap|kinetic|nuclear> calls of tests/hartree-fock/hartree-fock++.cc:
+ *      267-275 (Engine::compute1, engine.impl.h:181-561).  charges = natom x {Z, x, y, z} (host;
+ *      make_point_charges, :1064); S, T, V = nbf x nbf row-major, device (on_device = 1) or host. */
+int lb200_onebody(lb200_context* ctx, const lb200_basis* bs, int natom, const double* charges, double* S,
+                  double* T, double* V, int on_device);
+
 /* ---- density fitting: three-centre integrals (P|mu nu) as dense slabs and the two-centre metric (P|Q):
  *      the DF set-up of tests/hartree-fock/hartree-fock++.cc:2215-2262 (Zxy[ndf][n][n] via
  *      Engine::compute2<coulomb, xs_xx>(dfbs[s1], Shell::unit(), obs[s2], obs[s3])) and

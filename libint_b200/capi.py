@@ -63,6 +63,7 @@ SIGNATURES = {
     "lb200_fock_create": (C.c_int, [vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
+    "lb200_onebody": (C.c_int, [vp, vp, C.c_int, dp, vp, vp, vp, C.c_int]),
     "lb200_eri_product": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]),
     "lb200_df3c_create": (C.c_int, [vp, vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_df3c_destroy": (C.c_int, [vp]),
@@ -356,6 +357,24 @@ class Fock:
             self.close()
         except Exception:
             pass
+
+
+def onebody(ctx, basis, charges, device=False):
+    """S, T, V of `basis` with point charges [(Z, (x, y, z)), ...] on the GPU (lb200_onebody).
+    device=False: numpy arrays; True: torch CUDA tensors."""
+    ch = np.ascontiguousarray([[z, c[0], c[1], c[2]] for z, c in charges], dtype=np.float64).reshape(-1, 4)
+    n = basis.nbf
+    if device:
+        import torch
+        dev = torch.device("cuda", ctx.device)
+        M = [torch.empty((n, n), dtype=torch.float64, device=dev) for _ in range(3)]
+        ctx.check(load().lb200_onebody(ctx.h, basis.h, len(ch), _d(ch), vp(M[0].data_ptr()), vp(M[1].data_ptr()),
+                                       vp(M[2].data_ptr()), 1), "onebody")
+        return M
+    M = [np.empty((n, n)) for _ in range(3)]
+    ctx.check(load().lb200_onebody(ctx.h, basis.h, len(ch), _d(ch), vp(M[0].ctypes.data), vp(M[1].ctypes.data),
+                                   vp(M[2].ctypes.data), 0), "onebody")
+    return M
 
 
 def eri_product(ctx, bra, ket, b0, nb, k0, nk, out, screening=SCREEN_ORIGINAL, precision=0.0, pure_out=False):

@@ -111,3 +111,93 @@ class RHF:
         self.converged = ediff_rel <= conv and rms <= conv
         self.energy = ehf + self.enuc
         return self.energy
+
+
+class RHFDevice:
+    """The same driver with every step on the GPU: S, T, V from lb200_onebody, the
+    orthogonalizer and the Fock diagonalisation through cuSOLVER (torch.linalg.eigh), density, energy,
+    commutator and DIIS as torch tensors on the device, G(D) from the GPU FockBuilder with device
+    buffers -- per iteration only scalars (energy, error norm) reach the host.  `builder` is a
+    libint_b200.fock.FockBuilder (its context, basis and rank set-up are reused)."""
+
+    def __init__(self, obs, atoms, builder, charge=0):
+        import torch
+        from . import capi
+        self.torch = torch
+        self.obs, self.atoms, self.builder = obs, atoms, builder
+        self.dev = torch.device("cuda", builder.ctx.device)
+        nelec = sum(a.atomic_number for a in atoms) - charge
+        if nelec % 2:
+            raise ValueError("RHF needs an even number of electrons")
+        self.ndocc = nelec // 2
+        self.enuc = onebody.nuclear_repulsion(atoms)
+        builder.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+        self.S, self.T, self.V = capi.onebody(builder.ctx, builder.basis, charges, device=True)
+        self.H = self.T + self.V
+        w, U = torch.linalg.eigh(self.S)            # gensqrtinv, hartree-fock++.cc:1957-2006
+        keep = w >= w[-1] / 1e8
+        self.cond = float(w[-1] / w[keep][0])
+        self.rank = int(keep.sum())
+        self.X = U[:, keep] / torch.sqrt(w[keep])
+        self.history = []
+        self.energy = None
+        self.D = self._density(self.H)
+
+    def _density(self, F):
+        torch = self.torch
+        e, Cp = torch.linalg.eigh(self.X.T @ F @ self.X)
+        self.evals = e
+        self.C = self.X @ Cp
+        Co = self.C[:, :self.ndocc]
+        return Co @ Co.T
+
+    def run(self, conv=1e-12, maxiter=100, verbose=False):
+        torch = self.torch
+        H, S = self.H, self.S
+        n2 = H.numel()
+        xs, es = [], []          # DIIS history (libint2::DIIS, start 2, depth 5)
+        D = self.D
+        ehf, rms, it = 0.0, 1.0, 0
+        eps = float(np.finfo(float).eps)
+        while True:
+            it += 1
+            ehf_last = ehf
+            precision = min(min(1e-3 / self.cond, 1e-7), max(rms / 1e4, eps))
+            F = H + self.builder(D, precision)
+            ehf = float((D * (H + F)).sum())
+            ediff_rel = abs((ehf - ehf_last) / ehf)
+            comm = F @ D @ S - S @ D @ F
+            rms = float(torch.linalg.norm(comm)) / n2
+            xs.append(F.clone())
+            es.append(comm)
+            if len(xs) > 5:
+                xs.pop(0)
+                es.pop(0)
+            Fx = F
+            n = len(xs)
+            if it >= 2 and n >= 2:
+                E = torch.stack([e.reshape(-1) for e in es])
+                B = torch.empty((n + 1, n + 1), dtype=torch.float64, device=self.dev)
+                B[:n, :n] = E @ E.T
+                B[:n, :n] /= max(float(B[:n, :n].abs().max()), 1e-300)
+                B[n, :n] = -1.0
+                B[:n, n] = -1.0
+                B[n, n] = 0.0
+                rhs = torch.zeros(n + 1, dtype=torch.float64, device=self.dev)
+                rhs[n] = -1.0
+                try:
+                    c = torch.linalg.solve(B, rhs)[:n]
+                    Fx = sum(ci * xi for ci, xi in zip(c, xs))
+                except RuntimeError:
+                    Fx = F
+            D = self._density(Fx)
+            self.history.append((it, ehf + self.enuc, ediff_rel, rms))
+            if verbose:
+                print(" %02d %20.12f %20.12e %20.12e" % self.history[-1])
+            if not ((ediff_rel > conv or rms > conv) and it < maxiter):
+                break
+        self.D, self.F = D, F
+        self.converged = ediff_rel <= conv and rms <= conv
+        self.energy = ehf + self.enuc
+        return self.energy

@@ -47,9 +47,17 @@ inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
 // STANDARD ordering (cgshell_ordering.h): x exponent runs l..0, then y runs (l-x)..0
 inline int cart_index(int l, int x, int y) { return ((l - x + 1) * (l - x)) / 2 + l - x - y; }
 
+// Index algebra of the Cartesian components, tabulated once: the recurrences below look their
+// operands up here instead of recomputing quantum numbers per element.
+constexpr int kTabL = kMaxL + 2;                       // shells 0 .. kMaxL+1
+constexpr int kTabN = (kTabL + 1) * (kTabL + 2) / 2;   // components of the largest tabulated shell
 struct CartTable {
   // xyz[l][idx][0..2]
   std::vector<std::vector<std::vector<int>>> xyz;
+  short q[kTabL + 1][kTabN][3];    // quantum numbers
+  short dir[kTabL + 1][kTabN];     // build direction: first of x,y,z with a nonzero quantum number
+  short dec[kTabL + 1][kTabN][3];  // index (in shell l-1) of the component with q[d]-1, -1 if q[d] == 0
+  short inc[kTabL + 1][kTabN][3];  // index (in shell l+1) of the component with q[d]+1
   CartTable() {
     xyz.resize(kMaxL + 2);
     for (int l = 0; l <= kMaxL + 1; ++l) {
@@ -57,7 +65,18 @@ struct CartTable {
       for (int x = l; x >= 0; --x)
         for (int y = l - x; y >= 0; --y) {
           const int z = l - x - y;
-          xyz[l][cart_index(l, x, y)] = {x, y, z};
+          const int i = cart_index(l, x, y);
+          xyz[l][i] = {x, y, z};
+          const int qq[3] = {x, y, z};
+          for (int d = 0; d < 3; ++d) {
+            q[l][i][d] = (short)qq[d];
+            int m[3] = {x, y, z}, p[3] = {x, y, z};
+            --m[d];
+            ++p[d];
+            dec[l][i][d] = qq[d] > 0 ? (short)cart_index(l - 1, m[0], m[1]) : (short)-1;
+            inc[l][i][d] = (short)cart_index(l + 1, p[0], p[1]);
+          }
+          dir[l][i] = (short)(x ? 0 : (y ? 1 : 2));
         }
     }
   }
@@ -136,19 +155,15 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
     for (int e = 1; e <= emax; ++e) {
       const int nm = nmv[e][0];
       for (int ie = 0; ie < ncart(e); ++ie) {
-        const auto& q = ct.xyz[e][ie];
-        const int d = build_dir(q);
-        int qm1[3] = {q[0], q[1], q[2]};
-        --qm1[d];
-        const int im1 = cart_index(e - 1, qm1[0], qm1[1]);
+        const int d = ct.dir[e][ie];
+        const int qm1d = ct.q[e][ie][d] - 1;
+        const int im1 = ct.dec[e][ie][d];
         const double* s1 = V + off[e - 1][0] + im1 * nmv[e - 1][0];
         double* t = V + off[e][0] + ie * nm;
-        if (qm1[d] > 0) {
-          int qm2[3] = {qm1[0], qm1[1], qm1[2]};
-          --qm2[d];
-          const int im2 = cart_index(e - 2, qm2[0], qm2[1]);
+        if (qm1d > 0) {
+          const int im2 = ct.dec[e - 1][im1][d];
           const double* s2 = V + off[e - 2][0] + im2 * nmv[e - 2][0];
-          const double fac = qm1[d] * oo2z;
+          const double fac = qm1d * oo2z;
           for (int m = 0; m < nm; ++m) {
             double val = WP[d] * s1[m + 1] + fac * (s2[m] - roz * s2[m + 1]);
             if (!unit_b) val += PA[d] * s1[m];
@@ -170,13 +185,10 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
       for (int e = 0; e <= emax; ++e) {
         const int nm = nmv[e][f];
         for (int ie = 0; ie < ncart(e); ++ie) {
-          const auto& qe = ct.xyz[e][ie];
           for (int jf = 0; jf < nf; ++jf) {
-            const auto& q = ct.xyz[f][jf];
-            const int d = build_dir(q);
-            int qm1[3] = {q[0], q[1], q[2]};
-            --qm1[d];
-            const int jm1 = cart_index(f - 1, qm1[0], qm1[1]);
+            const int d = ct.dir[f][jf];
+            const int qm1d = ct.q[f][jf][d] - 1;
+            const int jm1 = ct.dec[f][jf][d];
             const double* s1 = V + off[e][f - 1] + (ie * nfm1 + jm1) * nmv[e][f - 1];
             double* t = V + off[e][f] + (ie * nf + jf) * nm;
             for (int m = 0; m < nm; ++m) {
@@ -184,21 +196,18 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
               if (!unit_d) val += QC[d] * s1[m];
               t[m] = val;
             }
-            if (qm1[d] > 0) {
-              int qm2[3] = {qm1[0], qm1[1], qm1[2]};
-              --qm2[d];
-              const int jm2 = cart_index(f - 2, qm2[0], qm2[1]);
+            if (qm1d > 0) {
+              const int jm2 = ct.dec[f - 1][jm1][d];
               const double* s2 = V + off[e][f - 2] + (ie * nfm2 + jm2) * nmv[e][f - 2];
-              const double fac = qm1[d] * oo2e;
+              const double fac = qm1d * oo2e;
               for (int m = 0; m < nm; ++m) t[m] += fac * (s2[m] - roe * s2[m + 1]);
             }
-            if (qe[d] > 0) {
-              int em1[3] = {qe[0], qe[1], qe[2]};
-              --em1[d];
-              const int iem1 = cart_index(e - 1, em1[0], em1[1]);
+            const int qed = ct.q[e][ie][d];
+            if (qed > 0) {
+              const int iem1 = ct.dec[e][ie][d];
               const double* s4 =
                   V + off[e - 1][f - 1] + (iem1 * nfm1 + jm1) * nmv[e - 1][f - 1];
-              const double fac = qe[d] * oo2ze;
+              const double fac = qed * oo2ze;
               for (int m = 0; m < nm; ++m) t[m] += fac * s4[m + 1];
             }
           }
@@ -268,16 +277,10 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
           const double* hi = cur + curoff[c + 1 - lc];  // (e0| c+1, dd-1)
           for (int ie = 0; ie < ne; ++ie)
             for (int ic = 0; ic < ncc; ++ic) {
-              const auto& qc = ct.xyz[c][ic];
               for (int id = 0; id < ndd; ++id) {
-                const auto& qd = ct.xyz[dd][id];
-                const int dir = build_dir(qd);
-                int dm1[3] = {qd[0], qd[1], qd[2]};
-                --dm1[dir];
-                int cp1[3] = {qc[0], qc[1], qc[2]};
-                ++cp1[dir];
-                const int idm1 = cart_index(dd - 1, dm1[0], dm1[1]);
-                const int icp1 = cart_index(c + 1, cp1[0], cp1[1]);
+                const int dir = ct.dir[dd][id];
+                const int idm1 = ct.dec[dd][id][dir];
+                const int icp1 = ct.inc[c][ic][dir];
                 out[((size_t)ie * ncc + ic) * ndd + id] =
                     hi[((size_t)ie * ncp1 + icp1) * ndm1 + idm1] +
                     CD[dir] * lo[((size_t)ie * ncc + ic) * ndm1 + idm1];
@@ -313,16 +316,10 @@ void build_generic(const Libint_t* inteval, int la, int lb, int lc, int ld, bool
         const double* lo = cur + curoff[a - la];
         const double* hi = cur + curoff[a + 1 - la];
         for (int ia = 0; ia < naa; ++ia) {
-          const auto& qa = ct.xyz[a][ia];
           for (int ib = 0; ib < nbb; ++ib) {
-            const auto& qb = ct.xyz[bb][ib];
-            const int dir = build_dir(qb);
-            int bm1[3] = {qb[0], qb[1], qb[2]};
-            --bm1[dir];
-            int ap1[3] = {qa[0], qa[1], qa[2]};
-            ++ap1[dir];
-            const int ibm1 = cart_index(bb - 1, bm1[0], bm1[1]);
-            const int iap1 = cart_index(a + 1, ap1[0], ap1[1]);
+            const int dir = ct.dir[bb][ib];
+            const int ibm1 = ct.dec[bb][ib][dir];
+            const int iap1 = ct.inc[a][ia][dir];
             const double* h = hi + ((size_t)iap1 * nbm1 + ibm1) * ncd;
             const double* l = lo + ((size_t)ia * nbm1 + ibm1) * ncd;
             double* ov = out + ((size_t)ia * nbb + ib) * ncd;

@@ -174,3 +174,40 @@ def test_hartree_fock_cli_fails_loudly_without_gpu():
                        text=True, cwd=root, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     assert "Hartree-Fock energy" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_onebody_device_matches_host(ctx):
+    """lb200_onebody (S, T, V on the GPU; Engine::compute1 of hartree-fock++.cc:267-275) against the host
+    McMurchie-Davidson evaluation that reproduces the golden energies, pure d/f and Cartesian shells."""
+    from libint_b200 import capi, onebody
+    from libint_b200.basis import BasisSet
+    atoms = _atoms("h2o_rotated")
+    for name, pure in (("cc-pvdz", None), ("def2-tzvp", None), ("6-31g*", None), ("cc-pvdz", True)):
+        bs = BasisSet(name, atoms)
+        if pure is not None:
+            bs.set_pure(pure)
+        B = capi.Basis(ctx, *bs.flat())
+        charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+        S, T, V = capi.onebody(ctx, B, charges)
+        Sh, Th, Vh = onebody.compute_1body_ints(bs, atoms)
+        np.testing.assert_allclose(S, Sh, rtol=1e-12, atol=1e-13, err_msg=name)
+        np.testing.assert_allclose(T, Th, rtol=1e-12, atol=1e-12, err_msg=name)
+        np.testing.assert_allclose(V, Vh, rtol=1e-12, atol=1e-12, err_msg=name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,geom,eref", GOLDEN)
+def test_device_scf_golden_energy(ctx, name, geom, eref):
+    """the whole RHF loop on the device (RHFDevice: GPU one-body integrals, cuSOLVER eigensolves, GPU
+    Fock builds with device buffers) reproduces the reference's golden energies to 1e-10 Eh."""
+    from libint_b200.basis import BasisSet
+    from libint_b200.fock import FockBuilder
+    from libint_b200.scf import RHFDevice
+    atoms = _atoms(geom)
+    bs = BasisSet(name, atoms)
+    fb = FockBuilder(bs, ctx=ctx, rank=0, nranks=1)
+    scf = RHFDevice(bs, atoms, fb)
+    e = scf.run()
+    assert scf.converged
+    assert abs(e - eref) < ETOL, "%s: %.12f vs %.12f" % (name, e, eref)
