@@ -181,7 +181,8 @@ def main():
     ap.add_argument("--quartets", type=int, default=10_000_000, help="quartets per class per step")
     ap.add_argument("--npairs", type=int, default=4096, help="bra / ket shell pairs per class")
     ap.add_argument("--chunk", type=int, default=1 << 20, help="quartets per launch")
-    ap.add_argument("--e2e-quartets", type=int, default=1 << 19, help="quartets per class in the host-buffer leg")
+    ap.add_argument("--e2e-quartets", type=int, default=10_000_000,
+                    help="quartets per class in the host-buffer leg (default: the full configs[1] workload)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--parity-quartets", type=int, default=20000, help="quartets per class checked against the arbiter")
     ap.add_argument("--no-fock", action="store_true")
@@ -354,7 +355,7 @@ def main():
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    nrep = max(1, min(args.steps, 3))
+    nrep = max(1, min(args.steps, 2))
     for _ in range(nrep):
         e2e_step()
     barrier()

@@ -116,12 +116,12 @@ cudaError_t launch_class(const EriParams& p, const RowInfo* rows, int num_sms,
     q.transpose_out = p.transpose_out ^ 1;
     if constexpr (RR<LC, LD, LA, LB>::NEC > 1) {
       if (p.uncontracted) {
-        // Fock mode: measured on (H2O)_64/def2-TZVP the pipelined kernel wins only for the
-        // (ps| row classes (5-15 %); with more rows per quartet the digestion's shared-memory and
-        // register footprint costs more than the hidden latency gains, so those stay general
+        // Fock mode: the pipelined kernel up to 35 rows per quartet.  Round 1 measured a gain only for the
+        // (ps| row classes; with 64-byte records and the Boys recursion it now wins (a little) everywhere:
+        // (H2O)_64 def2-TZVP 2.288 -> 2.245 s, cc-pVTZ 5.538 -> 5.387 s for MAXNEC 4 -> 35 (56 / 84: no change)
         if constexpr (MODE == kModeFock) {
 #ifndef LB200_FOCK_PRIM_MAXNEC
-#define LB200_FOCK_PRIM_MAXNEC 4
+#define LB200_FOCK_PRIM_MAXNEC 35
 #endif
           if constexpr (RR<LC, LD, LA, LB>::NEC <= LB200_FOCK_PRIM_MAXNEC)
             return launch_rowreg_prim_tr<LC, LD, LA, LB, false, true>(q, rows, num_sms, stream);

@@ -1,0 +1,9 @@
+for v in "" _head "" _head; do
+LB200_LIB_SUFFIX=$v python bench.py --no-fock --no-df3c --no-cpu-baseline --steps 5 2>/dev/null | python -c "
+import json,sys
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        b=json.loads(ln); p=b['per_class']
+        print('variant [$v]', round(b['ms_per_step'],2), {k:round(p[k]['ms'],2) for k in ('2222','2122','2121','1122','1111','1010','0000')})
+"
+done
