@@ -152,7 +152,11 @@ class RHFDevice:
         Co = self.C[:, :self.ndocc]
         return Co @ Co.T
 
-    def run(self, conv=1e-12, maxiter=100, verbose=False):
+    def run(self, conv=1e-12, maxiter=100, verbose=False, incremental=True):
+        """incremental=True: the reference's incremental Fock formation (hartree-fock++.cc:420-480): once
+        the error is below 1e-5, F += G(D - D_last) with a density difference whose shell-block norms -- and
+        so the number of quartets surviving the Schwarz x density screen -- shrink from iteration to
+        iteration; reset to a full build when the error fell 10x or after 8 iterations."""
         torch = self.torch
         H, S = self.H, self.S
         n2 = H.numel()
@@ -160,15 +164,38 @@ class RHFDevice:
         D = self.D
         ehf, rms, it = 0.0, 1.0, 0
         eps = float(np.finfo(float).eps)
+        D_diff, F = D, H
+        reset, started = False, False
+        start_thr = 1e-5 if incremental else 0.0
+        next_reset_thr, last_reset_it = 0.0, 0
+        self.full_builds = self.incremental_builds = 0
         while True:
             it += 1
             ehf_last = ehf
+            D_last = D
+            if not started and rms < start_thr:
+                started, reset = True, False
+                last_reset_it = it - 1
+                next_reset_thr = rms / 10.0
+            if reset or not started:
+                F = H
+                D_diff = D
+            if reset and started:
+                reset = False
+                last_reset_it = it
+                next_reset_thr = rms / 10.0
             precision = min(min(1e-3 / self.cond, 1e-7), max(rms / 1e4, eps))
-            F = H + self.builder(D, precision)
+            if D_diff is D:
+                self.full_builds += 1
+            else:
+                self.incremental_builds += 1
+            F = F + self.builder(D_diff, precision)
             ehf = float((D * (H + F)).sum())
             ediff_rel = abs((ehf - ehf_last) / ehf)
             comm = F @ D @ S - S @ D @ F
             rms = float(torch.linalg.norm(comm)) / n2
+            if rms < next_reset_thr or it - last_reset_it >= 8:
+                reset = True
             xs.append(F.clone())
             es.append(comm)
             if len(xs) > 5:
@@ -192,6 +219,7 @@ class RHFDevice:
                 except RuntimeError:
                     Fx = F
             D = self._density(Fx)
+            D_diff = D - D_last
             self.history.append((it, ehf + self.enuc, ediff_rel, rms))
             if verbose:
                 print(" %02d %20.12f %20.12e %20.12e" % self.history[-1])

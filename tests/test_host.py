@@ -122,3 +122,46 @@ def test_engine_argument_errors():
         E.Engine(E.Operator.coulomb, 1, 7, ctx=object())
     with pytest.raises(NotImplementedError):
         E.Engine(E.Operator.coulomb, 1, 1, deriv_order=1, ctx=object())
+
+
+def test_iface_library_exports_the_reference_boundary():
+    """liblibint_b200_iface.so loads without a GPU and exports every symbol of the reference's generated
+    C interface (src/bin/libint/iface.cc:114-185,302-418) that include/libint2/util/generated/libint2_iface.h
+    declares; the function tables are dimensioned by the MAX_AM macros of libint2_params.h and canonical
+    entries are filled by libint2_static_init (null = no kernel, engine.impl.h:1898)."""
+    from libint_b200 import capi
+    inc = os.path.join(ROOT, "include", "libint2", "util", "generated")
+    hdr = open(os.path.join(inc, "libint2_iface.h")).read()
+    names = set(re.findall(r"\b(libint2_[a-z0-9_]+)\s*[\[(]", hdr))
+    assert {"libint2_build_eri", "libint2_build_3eri", "libint2_build_2eri", "libint2_build_default",
+            "libint2_static_init", "libint2_static_cleanup", "libint2_init_eri", "libint2_need_memory_eri",
+            "libint2_cleanup_eri", "libint2_init_default", "libint2_cleanup_default"} <= names
+    path = os.path.join(os.path.dirname(capi.LIB_PATH), "liblibint_b200_iface.so")
+    L = ctypes.CDLL(path)
+    for n in sorted(names):
+        assert hasattr(L, n), "missing export " + n
+    params = open(os.path.join(inc, "libint2_params.h")).read()
+    am = {k: int(v) for k, v in re.findall(r"#define LIBINT2_MAX_AM_(\w+) (\d+)", params)}
+    assert am == {"default": 4, "eri": 3, "3eri": 4, "2eri": 4}
+    L.libint2_need_memory_eri.restype = ctypes.c_size_t
+    L.libint2_need_memory_eri.argtypes = [ctypes.c_int]
+    assert L.libint2_need_memory_eri(2) >= 6 ** 4
+    # static_init fills the canonical classes without touching the GPU
+    L.libint2_static_init()
+    n4 = am["eri"] + 1
+    tab = (ctypes.c_void_p * (n4 ** 4)).in_dll(L, "libint2_build_eri")
+    idx = lambda a, b, c, d: ((a * n4 + b) * n4 + c) * n4 + d
+    assert tab[idx(0, 0, 0, 0)] is None            # (ss|ss) is done by the Engine itself (engine.impl.h:1890)
+    assert tab[idx(1, 0, 1, 0)] and tab[idx(2, 2, 2, 2)] and tab[idx(3, 3, 3, 3)] and tab[idx(1, 1, 3, 0)]
+    assert tab[idx(1, 1, 1, 0)] is None            # not canonical: la + lb > lc + ld (build_libint.cc:78-83)
+    assert tab[idx(0, 1, 1, 1)] is None            # not canonical: la < lb
+
+
+def test_generated_iface_headers_are_current(tmp_path):
+    """include/libint2/util/generated/*.h are what tools/gen_iface_headers.py writes."""
+    import importlib
+    gen = importlib.import_module("libint_b200.tools.gen_iface_headers")
+    inc = os.path.join(ROOT, "include", "libint2", "util", "generated")
+    for name, text in (("libint2_params.h", gen.params()), ("libint2_types.h", gen.types()),
+                       ("libint2_iface.h", gen.iface())):
+        assert open(os.path.join(inc, name)).read() == text, name + " is stale: run tools/gen_iface_headers.py"

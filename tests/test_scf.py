@@ -211,3 +211,7 @@ def test_device_scf_golden_energy(ctx, name, geom, eref):
     e = scf.run()
     assert scf.converged
     assert abs(e - eref) < ETOL, "%s: %.12f vs %.12f" % (name, e, eref)
+    assert scf.incremental_builds > 0 and scf.full_builds > 1   # hartree-fock++.cc:420-480 schedule was exercised
+    scf2 = RHFDevice(bs, atoms, fb)
+    e2 = scf2.run(incremental=False)
+    assert scf2.incremental_builds == 0 and abs(e2 - eref) < ETOL
