@@ -70,11 +70,18 @@ struct RR {
   // decides the bank pattern: with stride = NEC (mod 16 eight-byte banks) a half-warp's
   // quartets tile the banks (row-indexed accesses) or land in distinct banks (broadcast
   // accesses); a stride that is a multiple of 16 would serialise every access QPG ways.
+  // CTA-wide groups (NEC > 16): stride = 2 (mod 16 banks) measured best of the eight even residues on the
+  // sweep ((dd|dd) 37.7 -> 37.2 ms, (dp|dd) 18.6 -> 18.1, (dp|dp) 11.8 -> 11.4 per 10^7 quartets)
+#ifndef LB200_PAD_WIDE
+#define LB200_PAD_WIDE 2
+#endif
   static constexpr int pad_stride(int s) {
     s = (s + 1) & ~1;
     if (NEC > 1 && NEC <= 16) {
       const int want = (NEC + (NEC & 1)) % 16;
       while (s % 16 != want) s += 2;
+    } else if (NEC > 16 && LB200_PAD_WIDE >= 0) {
+      while (s % 16 != LB200_PAD_WIDE) s += 2;
     }
     return s;
   }
