@@ -172,6 +172,31 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
                      int use_schwarz, int rank, int nranks, double* G, int G_on_device,
                      double* stats);
 
+/* ---- first geometric derivatives: batched Engine::compute2<Operator::coulomb, BraKet::xx_xx, 1>
+ *      (engine.impl.h:1151-2113 with deriv_order 1; hartree-fock++.cc:1978).  Same arguments as lb200_eri_batch;
+ *      output: ntasks x 12 blocks of n_a*n_b*n_c*n_d doubles, block d = 3 * centre + xyz with the centres in
+ *      the order (bra.first, bra.second, ket.first, ket.second) -- Engine::results()[0..11].  Built from the
+ *      ordinary class kernels with one angular momentum shifted (d/dA_x (ab|cd) = 2 alpha_a (a+1_x b|cd) -
+ *      a_x (a-1_x b|cd), src/bin/test_eri/eri.h:383-460), fourth centre by translational invariance; a class
+ *      whose raised twins have no kernel (l = 3 next to l >= 1) returns LB200_ERR_LMAX -- the analogue of
+ *      LIBINT2_MAX_AM_eri1 < LIBINT2_MAX_AM_eri.  Four-centre blocks only (no Shell::unit()). */
+/* the six shifted shell sets a class (la lb|lc ld), la >= lb, lc >= ld, is differentiated from -- A+, A-, B+, B-,
+ * C+, C- -- as 5 integers each: doubles per task (0: the lowered shell does not exist) and the strides of the
+ * component indices (a, b, c, d) inside a block.  Host-only; LB200_ERR_LMAX as lb200_eri_deriv1_batch. */
+int lb200_eri_deriv1_plan(int la, int lb, int lc, int ld, long long* plan /* 30 */);
+int lb200_eri_deriv1_batch(lb200_context* ctx, const lb200_pairs* bra, const lb200_pairs* ket,
+                           long long ntasks, const int* tasks, int tasks_on_device, int screening,
+                           double precision, int pure_out, double* out, int out_on_device);
+
+/* ---- two-body forces of the direct SCF driver: F2[3 * atom + xyz] = sum_ij G1[3 atom + xyz]_ij D_ij with
+ *      G1 = compute_2body_fock_deriv<1>(obs, atoms, D) (hartree-fock++.cc:1775-2055, used at :648-656),
+ *      evaluated on the GPU without forming the 3 * natoms matrices G1: same quartets, screening and rank
+ *      ownership as lb200_fock_build; shell2atom[nshell] = BasisSet::shell2atom(atoms); grad = 3 * natoms
+ *      doubles (host).  With nranks > 1 every rank returns a partial gradient to be summed.
+ *      stats (optional, 3 doubles): shell quartets, kernel launches, device milliseconds. */
+int lb200_fock_grad(lb200_fock* f, const double* D, int D_on_device, double precision, int use_schwarz,
+                    int rank, int nranks, int natoms, const int* shell2atom, double* grad, double* stats);
+
 /* ---- batched Engine::compute2 over an implicit Cartesian product of pair ranges: task t =
  *      (bra pair b0 + t / nk, ket pair k0 + t % nk), t < nb * nk -- no task list is built or read
  *      (the three-centre sweep and the two-centre metric are such products).  Device output only. */

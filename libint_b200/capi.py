@@ -53,6 +53,10 @@ SIGNATURES = {
     "lb200_pairs_get": (C.c_int, [vp, C.c_int, dp, C.c_int]),
     "lb200_eri_batch": (C.c_int, [vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_double,
                                   C.c_int, vp, C.c_int]),
+    "lb200_eri_deriv1_batch": (C.c_int, [vp, vp, vp, C.c_longlong, vp, C.c_int, C.c_int, C.c_double,
+                                         C.c_int, vp, C.c_int]),
+    "lb200_eri_deriv1_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "lb200_fock_grad": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, ip, dp, dp]),
     "lb200_eri_prereq_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, ip, dp, dp, dp]),
     "lb200_eri_block_size": (C.c_longlong, [vp, vp, C.c_int]),
     "lb200_eri_class_supported": (C.c_int, [C.c_int] * 4),
@@ -279,6 +283,33 @@ def eri_batch(ctx, bra, ket, tasks, out=None, screening=SCREEN_ORIGINAL, precisi
     return out
 
 
+def eri_deriv1_plan(la, lb, lc, ld):
+    """(6, 5) int64: per shifted set A+, A-, B+, B-, C+, C- the doubles per task and the strides of the
+    (a, b, c, d) component indices (lb200_eri_deriv1_plan)."""
+    plan = (C.c_longlong * 30)()
+    rc = load().lb200_eri_deriv1_plan(int(la), int(lb), int(lc), int(ld), plan)
+    if rc != OK:
+        raise Lb200Error("lb200_eri_deriv1_plan(%d%d|%d%d) failed (%d)" % (la, lb, lc, ld, rc))
+    return np.array(list(plan), dtype=np.int64).reshape(6, 5)
+
+
+def eri_deriv1_batch(ctx, bra, ket, tasks, out=None, screening=SCREEN_ORIGINAL, precision=0.0,
+                     pure_out=False):
+    """Batched Engine::compute2<coulomb, xx_xx, 1>: out[n, 12, block]; block d = 3 * centre + xyz, centres
+    in the order (bra.first, bra.second, ket.first, ket.second)."""
+    blk = eri_block_size(bra, ket, pure_out)
+    if isinstance(tasks, np.ndarray):
+        tasks = np.ascontiguousarray(tasks, dtype=np.int32).reshape(-1, 2)
+    n = tasks.shape[0]
+    if out is None:
+        out = np.empty((n, 12, blk))
+    tp, tdev = _ptr(tasks)
+    op, odev = _ptr(out)
+    ctx.check(load().lb200_eri_deriv1_batch(ctx.h, bra.h, ket.h, n, tp, tdev, int(screening),
+                                            float(precision), int(pure_out), op, odev), "eri_deriv1_batch")
+    return out
+
+
 def significant_pairs(bs, threshold=1e-12, device=True):
     """obs_shellpair_list of the reference (hartree-fock++.cc:1305-1381) as two int32 arrays (s1 >= s2).
     device=True: evaluated by a GPU kernel on the basis' context; False: the serial host loop."""
@@ -335,6 +366,23 @@ class Fock:
         if stats:
             return out, {"nquartets": st[0], "launches": st[1], "ms": st[2], "candidates": st[3]}
         return out
+
+    def gradient(self, D, shell2atom, natoms, precision, use_schwarz=True, rank=0, nranks=1, stats=False):
+        """two-body forces F2[natoms, 3] = sum_ij G1[3 atom + xyz]_ij D_ij (compute_2body_fock_deriv<1> of the
+        reference contracted with D, hartree-fock++.cc:648-656) -- the partial sum of this rank's quartets"""
+        if isinstance(D, np.ndarray):
+            D = np.ascontiguousarray(D, dtype=np.float64)
+        Dp, Ddev = _ptr(D)
+        s2a = np.ascontiguousarray(shell2atom, dtype=np.int32)
+        if len(s2a) != self.obs.nshell:
+            raise ValueError("shell2atom needs one entry per shell")
+        g = np.zeros((int(natoms), 3))
+        st = np.zeros(3)
+        self.ctx.check(load().lb200_fock_grad(self.h, Dp, Ddev, float(precision), int(use_schwarz), int(rank),
+                                              int(nranks), int(natoms), _i(s2a), _d(g), _d(st)), "fock_grad")
+        if stats:
+            return g, {"nquartets": st[0], "launches": st[1], "ms": st[2]}
+        return g
 
     def set_profile(self, on=True):
         load().lb200_fock_set_profile(self.h, int(bool(on)))

@@ -130,7 +130,7 @@ int lb200_context_destroy(lb200_context* ctx) {
   cudaFree(ctx->d_sph_col);
   cudaFree(ctx->d_sph_val);
   cudaFree(ctx->d_sph_base);
-  for (int i = 0; i < 5; ++i) cudaFree(ctx->d_scratch[i]);
+  for (int i = 0; i < lb200_context::kScratchSlots; ++i) cudaFree(ctx->d_scratch[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
@@ -246,9 +246,88 @@ int lb200_basis_shell2bf(const lb200_basis* bs, int* out) {
 
 namespace lb200 {
 
+// one device allocation: prim (+ K, p1p2 of device-built blocks) | geom | schwarz | prim_off | shell | gidx
+int upload_pairs(lb200_context* ctx, lb200_pairs* P, const std::vector<PairGeom>& geom,
+                 const double* pair_schwarz, bool with_prims) {
+  PairBlock& d = P->dev;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t n = (size_t)d.npair;
+  const size_t np = (size_t)P->nprim_total;
+  const size_t o_prim = 0, o_kraw = al(o_prim + np * sizeof(PrimPair));
+  const size_t o_pp = with_prims ? o_kraw : al(o_kraw + np * 8);
+  const size_t o_geom = with_prims ? o_kraw : al(o_pp + np * sizeof(int2));
+  const size_t o_sw = al(o_geom + n * sizeof(PairGeom)), o_po = al(o_sw + n * 8), o_sh = al(o_po + (n + 1) * 4);
+  const size_t o_gi = al(o_sh + 2 * n * 4), total = al(o_gi + n * 4) + 256;
+  cudaSetDevice(ctx->device);
+  int rc = check_cuda(ctx, cudaMalloc(&P->d_block, total), "cudaMalloc(pairs)");
+  if (rc) return rc;
+  char* base = static_cast<char*>(P->d_block);
+  std::vector<int> gidx(n);
+  for (size_t i = 0; i < n; ++i) {
+    const long long hi = std::max(P->shell[2 * i], P->shell[2 * i + 1]);
+    const long long lo = std::min(P->shell[2 * i], P->shell[2 * i + 1]);
+    gidx[i] = (int)(hi * (hi + 1) / 2 + lo);   // < 2^31 for < 65536 shells (checked by lb200_fock_create)
+  }
+  std::vector<double> sw(n, 0.0);
+  if (pair_schwarz) sw.assign(pair_schwarz, pair_schwarz + n);
+  if (with_prims)
+    cudaMemcpy(base + o_prim, P->prim.data(), np * sizeof(PrimPair), cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_geom, geom.data(), n * sizeof(PairGeom), cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_sw, sw.data(), n * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_po, P->prim_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_sh, P->shell.data(), 2 * n * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_gi, gidx.data(), n * 4, cudaMemcpyHostToDevice);
+  rc = check_cuda(ctx, cudaGetLastError(), "upload pairs");
+  if (rc) { cudaFree(P->d_block); P->d_block = nullptr; return rc; }
+  d.prim = reinterpret_cast<const PrimPair*>(base + o_prim);
+  d.geom = reinterpret_cast<const PairGeom*>(base + o_geom);
+  d.schwarz = reinterpret_cast<const double*>(base + o_sw);
+  d.prim_off = reinterpret_cast<const int*>(base + o_po);
+  d.shell = reinterpret_cast<const int*>(base + o_sh);
+  d.gidx = reinterpret_cast<const int*>(base + o_gi);
+  if (!with_prims) {
+    P->d_Kraw = reinterpret_cast<const double*>(base + o_kraw);
+    P->d_p1p2 = reinterpret_cast<const int2*>(base + o_pp);
+  }
+  return LB200_OK;
+}
+
+int ctx_scratch(lb200_context* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_scratch[slot]);
+    ctx->d_scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    int r = check_cuda(ctx, cudaMalloc(&ctx->d_scratch[slot], bytes), "cudaMalloc(scratch)");
+    if (r) return r;
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->d_scratch[slot];
+  return LB200_OK;
+}
+
+int pairs_host_mirror(const lb200_pairs* Pc) {
+  if (Pc->host_valid) return LB200_OK;
+  auto* P = const_cast<lb200_pairs*>(Pc);
+  const size_t np = (size_t)P->nprim_total;
+  cudaSetDevice(P->ctx->device);
+  P->prim.resize(np);
+  P->Kraw.resize(np);
+  P->p1p2.resize(2 * np);
+  cudaMemcpy(P->prim.data(), P->dev.prim, np * sizeof(PrimPair), cudaMemcpyDeviceToHost);
+  cudaMemcpy(P->Kraw.data(), P->d_Kraw, np * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(P->p1p2.data(), P->d_p1p2, np * sizeof(int2), cudaMemcpyDeviceToHost);
+  const int rc = check_cuda(P->ctx, cudaGetLastError(), "download pair records");
+  if (!rc) P->host_valid = true;
+  return rc;
+}
+
 // ShellPair::init, include/libint2/shell.h:1138-1256 (Original/Conservative) and
 // :1259-1328 (Schwarz variants), for a whole block of pairs; PA/gamma/c_a*c_b are the
 // per-quartet prerequisites of engine.impl.h:1331-1367,1514-1537 hoisted to the pair.
+// Blocks of at least LB200_PAIRS_DEVICE_MIN pairs (default 2048) run the primitive-pair loop on the GPU
+// (pairs_device.cu: count, prefix sum, fill); smaller ones on the host.
 int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* bs2, int npair,
                 const int* s1, const int* s2, int screening, double ln_prec,
                 const double* prim_schwarz, const double* pair_schwarz, lb200_pairs** out) {
@@ -271,6 +350,8 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
   }
   auto* P = new lb200_pairs;
   P->ctx = ctx;
+  P->alpha1 = bs1->alpha; P->off1 = bs1->off;
+  P->alpha2 = bs2->alpha; P->off2 = bs2->off;
   PairBlock& d = P->dev;
   d.npair = npair;
   if (npair > 0) {
@@ -284,7 +365,8 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
   P->shell.resize(2 * (size_t)npair);
   P->bf.resize(2 * (size_t)npair);
   P->AB.resize(3 * (size_t)npair);
-  size_t fac_off = 0;
+  P->A.resize(3 * (size_t)npair);
+  // ---- per pair: validation, geometry ---------------------------------------------------------
   for (int i = 0; i < npair; ++i) {
     const int a = s1[i], b = s2[i];
     if (a < 0 || a >= bs1->nshell || b < 0 || b >= bs2->nshell) {
@@ -299,19 +381,63 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     }
     P->shell[2 * i] = a; P->shell[2 * i + 1] = b;
     P->bf[2 * i] = bs1->shell2bf[a]; P->bf[2 * i + 1] = bs2->shell2bf[b];
-    const double* A = &bs1->O[3 * a];
-    const double* B = &bs2->O[3 * b];
-    double AB[3], AB2 = 0.;
-    for (int k = 0; k < 3; ++k) { AB[k] = A[k] - B[k]; AB2 += AB[k] * AB[k]; }
-    for (int k = 0; k < 3; ++k) P->AB[3 * i + k] = AB[k];
-    const int np1 = bs1->nprim[a], np2 = bs2->nprim[b];
-    const int l1 = bs1->l[a], l2 = bs2->l[b];
+    for (int k = 0; k < 3; ++k) {
+      P->A[3 * i + k] = bs1->O[3 * a + k];
+      P->AB[3 * i + k] = bs1->O[3 * a + k] - bs2->O[3 * b + k];
+    }
     const bool unit_b = bs2->is_unit(b);
     if (i == 0) d.unit_b = unit_b ? 1 : 0;
     if ((d.unit_b != 0) != unit_b) {
       delete P;
       return set_error(ctx, LB200_ERR_INVALID, "unit and ordinary second shells cannot share a block");
     }
+  }
+  const size_t n = (size_t)npair;
+  std::vector<PairGeom> geom(n);
+  for (size_t i = 0; i < n; ++i) {
+    PairGeom& g = geom[i];
+    for (int k = 0; k < 3; ++k) {
+      g.A[k] = bs1->O[3 * (size_t)P->shell[2 * i] + k];
+      g.AB[k] = P->AB[3 * i + k];
+    }
+    g.bf[0] = P->bf[2 * i]; g.bf[1] = P->bf[2 * i + 1];
+    g.shell[0] = P->shell[2 * i]; g.shell[1] = P->shell[2 * i + 1];
+  }
+  // ---- primitive pairs --------------------------------------------------------------------------
+  // read per call: tests build one block both ways
+  const char* env_min = std::getenv("LB200_PAIRS_DEVICE_MIN");
+  const int device_min = env_min ? std::atoi(env_min) : 2048;
+  if (npair >= device_min && npair > 0) {
+    DevicePrimBuilder bld;
+    int rc = bld.init(ctx, bs1, bs2, npair, s1, s2, screening, ln_prec, prim_schwarz);
+    std::vector<int> counts;
+    if (!rc) rc = bld.count(counts);
+    if (rc) { delete P; return rc; }
+    long long tot = 0;
+    for (int i = 0; i < npair; ++i) {
+      tot += counts[i];
+      if (tot > 0x7fffffffll) { delete P; return set_error(ctx, LB200_ERR_INVALID, "too many primitive pairs in one block"); }
+      P->prim_off[i + 1] = (int)tot;
+      d.max_nprim = std::max(d.max_nprim, counts[i]);
+    }
+    P->nprim_total = tot;
+    P->host_valid = false;
+    rc = upload_pairs(ctx, P, geom, pair_schwarz, false);
+    if (!rc) rc = bld.fill(d.prim_off, const_cast<PrimPair*>(d.prim), const_cast<double*>(P->d_Kraw),
+                           const_cast<int2*>(P->d_p1p2));
+    if (rc) { cudaFree(P->d_block); delete P; return rc; }
+    *out = P;
+    return LB200_OK;
+  }
+  size_t fac_off = 0;
+  for (int i = 0; i < npair; ++i) {
+    const int a = s1[i], b = s2[i];
+    const double* A = &bs1->O[3 * a];
+    const double* B = &bs2->O[3 * b];
+    double AB2 = 0.;
+    for (int k = 0; k < 3; ++k) AB2 += P->AB[3 * i + k] * P->AB[3 * i + k];
+    const int np1 = bs1->nprim[a], np2 = bs2->nprim[b];
+    const int l1 = bs1->l[a], l2 = bs2->l[b];
     for (int p1 = 0; p1 < np1; ++p1)
       for (int p2 = 0; p2 < np2; ++p2) {
         const double a1 = bs1->alpha[bs1->off[a] + p1], a2 = bs2->alpha[bs2->off[b] + p2];
@@ -372,48 +498,9 @@ int build_pairs(lb200_context* ctx, const lb200_basis* bs1, const lb200_basis* b
     P->prim_off[i + 1] = (int)P->prim.size();
     d.max_nprim = std::max(d.max_nprim, P->prim_off[i + 1] - P->prim_off[i]);
   }
-  // one device allocation: prim | geom | schwarz | prim_off | shell | gidx
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t n = (size_t)npair;
-  const size_t o_prim = 0, o_geom = al(o_prim + P->prim.size() * sizeof(PrimPair));
-  const size_t o_sw = al(o_geom + n * sizeof(PairGeom)), o_po = al(o_sw + n * 8), o_sh = al(o_po + (n + 1) * 4);
-  const size_t o_gi = al(o_sh + 2 * n * 4), total = al(o_gi + n * 4) + 256;
-  std::vector<PairGeom> geom(n);
-  for (size_t i = 0; i < n; ++i) {
-    PairGeom& g = geom[i];
-    for (int k = 0; k < 3; ++k) {
-      g.A[k] = bs1->O[3 * (size_t)P->shell[2 * i] + k];
-      g.AB[k] = P->AB[3 * i + k];
-    }
-    g.bf[0] = P->bf[2 * i]; g.bf[1] = P->bf[2 * i + 1];
-    g.shell[0] = P->shell[2 * i]; g.shell[1] = P->shell[2 * i + 1];
-  }
-  cudaSetDevice(ctx->device);
-  int rc = check_cuda(ctx, cudaMalloc(&P->d_block, total), "cudaMalloc(pairs)");
+  P->nprim_total = (long long)P->prim.size();
+  const int rc = upload_pairs(ctx, P, geom, pair_schwarz, true);
   if (rc) { delete P; return rc; }
-  char* base = static_cast<char*>(P->d_block);
-  std::vector<int> gidx(n);
-  for (size_t i = 0; i < n; ++i) {
-    const long long hi = std::max(P->shell[2 * i], P->shell[2 * i + 1]);
-    const long long lo = std::min(P->shell[2 * i], P->shell[2 * i + 1]);
-    gidx[i] = (int)(hi * (hi + 1) / 2 + lo);   // < 2^31 for < 65536 shells (checked by lb200_fock_create)
-  }
-  std::vector<double> sw(n, 0.0);
-  if (pair_schwarz) sw.assign(pair_schwarz, pair_schwarz + n);
-  cudaMemcpy(base + o_prim, P->prim.data(), P->prim.size() * sizeof(PrimPair), cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_geom, geom.data(), n * sizeof(PairGeom), cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_sw, sw.data(), n * 8, cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_po, P->prim_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_sh, P->shell.data(), 2 * n * 4, cudaMemcpyHostToDevice);
-  cudaMemcpy(base + o_gi, gidx.data(), n * 4, cudaMemcpyHostToDevice);
-  rc = check_cuda(ctx, cudaGetLastError(), "upload pairs");
-  if (rc) { cudaFree(P->d_block); delete P; return rc; }
-  d.prim = reinterpret_cast<const PrimPair*>(base + o_prim);
-  d.geom = reinterpret_cast<const PairGeom*>(base + o_geom);
-  d.schwarz = reinterpret_cast<const double*>(base + o_sw);
-  d.prim_off = reinterpret_cast<const int*>(base + o_po);
-  d.shell = reinterpret_cast<const int*>(base + o_sh);
-  d.gidx = reinterpret_cast<const int*>(base + o_gi);
   *out = P;
   return LB200_OK;
 }
@@ -494,6 +581,7 @@ int lb200_pairs_create(lb200_context* ctx, const lb200_basis* bs1, const lb200_b
 int lb200_pairs_destroy(lb200_pairs* p) {
   if (!p) return LB200_OK;
   cudaSetDevice(p->ctx->device);
+  free_deriv_blocks(p);
   cudaFree(p->d_block);
   delete p;
   return LB200_OK;
@@ -502,12 +590,13 @@ int lb200_pairs_destroy(lb200_pairs* p) {
 int lb200_pairs_info(const lb200_pairs* p, long long* info) {
   if (!p || !info) return LB200_ERR_INVALID;
   info[0] = p->dev.la; info[1] = p->dev.lb; info[2] = p->dev.npair;
-  info[3] = (long long)p->prim.size(); info[4] = p->dev.pure_a; info[5] = p->dev.pure_b;
+  info[3] = p->nprim_total; info[4] = p->dev.pure_a; info[5] = p->dev.pure_b;
   return LB200_OK;
 }
 
 int lb200_pairs_get(const lb200_pairs* p, int i, double* out, int cap) {
   if (!p || i < 0 || i >= p->dev.npair) return LB200_ERR_INVALID;
+  if (pairs_host_mirror(p)) return LB200_ERR_CUDA;
   const int b = p->prim_off[i], e = p->prim_off[i + 1];
   if (e - b > cap) return LB200_ERR_INVALID;
   for (int k = b; k < e; ++k) {

@@ -315,6 +315,17 @@ __global__ void symmetrize_kernel(const double* __restrict__ F, double* __restri
   }
 }
 
+struct DevArrays {   // device arrays of one call, freed on every exit path
+  std::vector<void*> p;
+  ~DevArrays() { for (void* x : p) cudaFree(x); }
+  template <class T> int get(lb200_context* c, T** out, size_t count) {
+    void* q = nullptr;
+    const int r = check_cuda(c, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)), "cudaMalloc(grad)");
+    if (!r) { p.push_back(q); *out = static_cast<T*>(q); }
+    return r;
+  }
+};
+
 }  // namespace
 
 namespace lb200 {
@@ -734,6 +745,179 @@ int lb200_fock_build(lb200_fock* f, const double* D, int D_on_device, double pre
     stats[1] = (double)(ctx->launches - launches0);
     stats[2] = ms;
     stats[3] = ncand;
+  }
+  return rc;
+}
+
+
+// Two-body forces: F2(atom, xyz) = sum_ij G1[3 atom + xyz]_ij D_ij with G1 = compute_2body_fock_deriv<1>
+// (hartree-fock++.cc:1775-2055, consumed at :648-656), evaluated without forming the 3 * natoms matrices:
+// the same quartets as the Fock build (same pair blocks, same screening kernel, same rank ownership), their
+// derivative shell sets from deriv.cu, contracted with the two-particle density on the fly.  Every quartet
+// runs at the tightest engine precision of the build (fock_precision / max|D|); the reference loosens it
+// per quartet (:1975-1977), which only drops primitives below that bound.
+int lb200_fock_grad(lb200_fock* f, const double* D, int D_on_device, double precision, int use_schwarz,
+                    int rank, int nranks, int natoms, const int* shell2atom, double* grad, double* stats) {
+  if (!f || !D || !grad || !shell2atom || natoms < 1 || nranks < 1 || rank < 0 || rank >= nranks)
+    return LB200_ERR_INVALID;
+  lb200_context* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const lb200_basis& obs = f->obs;
+  const int n = obs.nbf, ns = obs.nshell;
+  const size_t n2 = (size_t)n * n;
+  for (int s = 0; s < ns; ++s)
+    if (shell2atom[s] < 0 || shell2atom[s] >= natoms)
+      return set_error(ctx, LB200_ERR_INVALID, "shell2atom entry out of range");
+  int rc = LB200_OK;
+  if (!f->d_D) rc = check_cuda(ctx, cudaMalloc(&f->d_D, n2 * 8), "cudaMalloc(D)");
+  if (rc) return rc;
+  // Cartesian function offsets
+  std::vector<int> s2c(ns), c2s, hl(obs.l), hp(obs.pure);
+  int nbfc = 0;
+  for (int s = 0; s < ns; ++s) {
+    s2c[s] = nbfc;
+    for (int k = 0; k < nc(obs.l[s]); ++k) c2s.push_back(s);
+    nbfc += nc(obs.l[s]);
+  }
+  DevArrays dev;   // freed on every exit path
+  int *d_l = nullptr, *d_pure = nullptr, *d_s2c = nullptr, *d_c2s = nullptr, *d_s2a = nullptr;
+  double *d_Dc = nullptr, *d_grad = nullptr;
+  int2* d_tasks2 = nullptr;
+  const long long cap = 1ll << 22;   // tasks per screening chunk (the derivative sets are the memory hog)
+  if ((rc = dev.get(ctx, &d_l, ns)) || (rc = dev.get(ctx, &d_pure, ns)) || (rc = dev.get(ctx, &d_s2c, ns)) ||
+      (rc = dev.get(ctx, &d_c2s, nbfc)) || (rc = dev.get(ctx, &d_s2a, ns)) ||
+      (rc = dev.get(ctx, &d_Dc, (size_t)nbfc * nbfc)) || (rc = dev.get(ctx, &d_grad, 3 * (size_t)natoms)) ||
+      (rc = dev.get(ctx, &d_tasks2, (size_t)cap)))
+    return rc;
+  if (f->task_cap < cap) {
+    for (int k = 0; k < f->nstreams; ++k) {
+      cudaFree(f->d_tasks[k]);
+      f->d_tasks[k] = nullptr;
+      if ((rc = check_cuda(ctx, cudaMalloc(&f->d_tasks[k], cap * sizeof(int4)), "cudaMalloc(tasks)"))) return rc;
+    }
+    f->task_cap = cap;
+  }
+  struct Events {
+    cudaEvent_t e[2] = {nullptr, nullptr};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } evs;
+  cudaEventCreate(&evs.e[0]);
+  cudaEventCreate(&evs.e[1]);
+  cudaEventRecord(evs.e[0], st);
+  cudaMemcpyAsync(d_l, hl.data(), ns * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_pure, hp.data(), ns * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_s2c, s2c.data(), ns * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_c2s, c2s.data(), (size_t)nbfc * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_s2a, shell2atom, ns * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(f->d_D, D, n2 * 8, D_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(d_grad, 0, 3 * (size_t)natoms * 8, st);
+  cudaMemsetAsync(f->d_scalar, 0, 8, st);
+  shellblock_norm_kernel<<<std::min(1024, (ns * ns + 255) / 256), 256, 0, st>>>(
+      f->d_D, n, ns, f->d_shell2bf, f->d_shellsize, f->d_Dnorm);
+  absmax_kernel<<<std::min(1024, (ns * ns + 255) / 256), 256, 0, st>>>(f->d_Dnorm, (long long)ns * ns, f->d_scalar);
+  ctx->launches += 2;
+  for (auto& c : f->classes) {
+    const int np = c.pairs->dev.npair;
+    if (np == 0) continue;
+    pair_dnorm_kernel<<<std::min(1024, (np + 255) / 256), 256, 0, st>>>(c.pairs->dev.shell, np, f->d_Dnorm, ns, c.d_dn);
+    ++ctx->launches;
+  }
+  rc = check_cuda(ctx, launch_cartesianize_density(ctx, f->d_D, n, d_Dc, nbfc, ns, d_l, d_pure, f->d_shell2bf, d_s2c,
+                                                   d_c2s, st), "cartesianize density");
+  ++ctx->launches;
+  double Dmax = 0;
+  cudaMemcpyAsync(&Dmax, f->d_scalar, 8, cudaMemcpyDeviceToHost, st);
+  if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(st), "gradient: D norms");
+  if (rc) return rc;
+  const double fock_precision = precision;
+  const double needed_engine_precision = fock_precision / Dmax;   // hartree-fock++.cc:1797
+  const double thr_num = fock_precision / Dmax * (1.0 - 1e-12);
+  const long long launches0 = ctx->launches;
+  double nquartets = 0;
+  std::vector<unsigned> jmax;
+  int4* const d_ftasks = f->d_tasks[0];
+  unsigned* const d_count = f->d_count[0];
+  const size_t ncls = f->classes.size();
+  for (size_t X = 0; X < ncls && !rc; ++X)
+    for (size_t Y = 0; Y <= X && !rc; ++Y) {
+      const FockClass& B = f->classes[X];
+      const FockClass& Kt = f->classes[Y];
+      const int nb = B.pairs->dev.npair, nk = Kt.pairs->dev.npair;
+      if (nb == 0 || nk == 0) continue;
+      DerivSets ds;
+      if ((rc = deriv_plan(ctx, B.pairs, Kt.pairs, ds))) break;
+      jmax.assign(nb, (unsigned)nk);
+      if (use_schwarz) {
+        int lo = nk;
+        for (int i = 0; i < nb; ++i) {
+          const double thr = thr_num / B.schwarz[i];
+          while (lo > 0 && Kt.schwarz[lo - 1] < thr) --lo;
+          jmax[i] = (unsigned)lo;
+        }
+      }
+      // tasks of one derivative chunk: bounded by 1 GiB of shifted shell sets
+      const long long sub = std::max(1ll, std::min(cap, (1ll << 30) / (ds.doubles_per_task * 8)));
+      int row = 0;
+      while (row < nb && !rc) {
+        long long sum = 0;
+        int r1 = row;
+        while (r1 < nb && (r1 == row || sum + jmax[r1] <= cap)) sum += jmax[r1++];
+        if (sum > cap) return set_error(ctx, LB200_ERR_NOMEM, "task buffer too small for one row");
+        if (sum > 0) {
+          ScreenParams sp{};
+          sp.bra = B.pairs->dev; sp.ket = Kt.pairs->dev;
+          sp.same_class = (X == Y);
+          sp.row0 = row; sp.nrow = r1 - row;
+          sp.nket = nk; sp.thr_num = thr_num;
+          sp.Dnorm = f->d_Dnorm; sp.nshell = ns;
+          sp.bra_dn = B.d_dn; sp.ket_dn = Kt.d_dn;
+          sp.fock_precision = fock_precision; sp.use_schwarz = use_schwarz;
+          sp.ln_needed_engine_precision = std::log(needed_engine_precision);
+          sp.rank = rank; sp.nranks = nranks;
+          sp.tasks = d_ftasks; sp.count = d_count; sp.cap = (unsigned)cap;
+          cudaMemsetAsync(d_count, 0, 8, st);
+          const size_t row_bytes = 2 * (size_t)ns * sizeof(double);
+          sp.stage_rows = row_bytes <= (size_t)96 * 1024;
+          screen_kernel<<<std::min(ctx->num_sms * 16, sp.nrow), 128, sp.stage_rows ? row_bytes : 0, st>>>(sp);
+          ++ctx->launches;
+          rc = check_cuda(ctx, launch_unpack_tasks(d_ftasks, d_count, d_tasks2, st, cap), "unpack tasks");
+          ++ctx->launches;
+          unsigned cnt = 0;
+          cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, st);
+          if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(st), "gradient: screening");
+          if (rc) break;
+          nquartets += cnt;
+          for (long long t0 = 0; t0 < (long long)cnt && !rc; t0 += sub) {
+            const long long nt = std::min(sub, (long long)cnt - t0);
+            double* d_sets = nullptr;
+            if ((rc = ctx_scratch(ctx, 5, (size_t)nt * ds.doubles_per_task * 8, reinterpret_cast<void**>(&d_sets))))
+              break;
+            rc = deriv_eval(ctx, B.pairs, Kt.pairs, nt, d_tasks2 + t0, kScreenSchwarzInf, needed_engine_precision,
+                            d_sets, ds);
+            if (rc) break;
+            DerivGradParams gp;
+            gp.tasks = d_tasks2 + t0; gp.ftasks = d_ftasks + t0;
+            gp.bra_shell = B.pairs->dev.shell; gp.ket_shell = Kt.pairs->dev.shell;
+            gp.shell2cbf = d_s2c; gp.shell2atom = d_s2a;
+            gp.Dc = d_Dc; gp.nbfc = nbfc; gp.grad = d_grad;
+            rc = check_cuda(ctx, launch_deriv_grad(ds, nt, gp, st), "gradient contraction");
+            ++ctx->launches;
+          }
+        }
+        row = r1;
+      }
+    }
+  if (rc) return rc;
+  cudaMemcpyAsync(grad, d_grad, 3 * (size_t)natoms * 8, cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(evs.e[1], st);
+  rc = check_cuda(ctx, cudaStreamSynchronize(st), "fock gradient");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, evs.e[0], evs.e[1]);
+  if (stats) {
+    stats[0] = nquartets;
+    stats[1] = (double)(ctx->launches - launches0);
+    stats[2] = ms;
   }
   return rc;
 }

@@ -55,8 +55,11 @@ class Engine:
                  screening_method=ScreeningMethod.Original, ctx=None, device=0):
         if oper != Operator.coulomb:
             raise NotImplementedError("only Operator.coulomb is on the B200 path")
-        if deriv_order != 0:
-            raise NotImplementedError("only deriv_order 0 is on the B200 path")
+        if deriv_order not in (0, 1):
+            raise NotImplementedError("deriv_order 0 and 1 are on the B200 path")
+        if deriv_order == 1 and braket != BraKet.xx_xx:
+            raise NotImplementedError("first derivatives are built for BraKet.xx_xx")
+        self.deriv_order = int(deriv_order)
         if max_l > capi.MAX_AM:
             raise lmax_exceeded("max_l=%d exceeds LB200_MAX_AM=%d" % (max_l, capi.MAX_AM))
         self.ctx = ctx if ctx is not None else capi.Context(device)
@@ -64,7 +67,7 @@ class Engine:
         self.braket = braket
         self.screening_method = ScreeningMethod(screening_method)
         self.set_precision(precision)
-        self._results = [None]
+        self._results = [None] * (12 if deriv_order == 1 else 1)
         self._unit = None
 
     # Engine::set_precision, engine.h:809-826
@@ -128,6 +131,32 @@ class Engine:
         bra, sw_b, keep1 = self._pairs(s1, s2)
         ket, sw_k, keep2 = self._pairs(s3, s4)
         scr = self._checked_screening()
+        n = [s1.size(), s2.size(), s3.size(), s4.size()]
+        nb = [n[1], n[0]] if sw_b else [n[0], n[1]]
+        nk = [n[3], n[2]] if sw_k else [n[2], n[3]]
+        if self.deriv_order == 1:
+            # compute2<coulomb, xx_xx, 1>: twelve shell sets, index 3 * centre + xyz in the caller's shell
+            # order (the reference re-maps the index when it permutes shells, engine.impl.h:1996-2003)
+            if self.braket != BraKet.xx_xx:
+                raise NotImplementedError("first derivatives are built for BraKet.xx_xx")
+            if bra.nprimpair == 0 or ket.nprimpair == 0:
+                self._results = [None] * 12
+                return None
+            out = capi.eri_deriv1_batch(self.ctx, bra, ket, np.array([[0, 0]], dtype=np.int32),
+                                        screening=int(scr), precision=self.precision, pure_out=True)[0]
+            centre = [1, 0] if sw_b else [0, 1]
+            centre += [3, 2] if sw_k else [2, 3]
+            res = [None] * 12
+            for c_lib, c_user in enumerate(centre):
+                for xyz in range(3):
+                    t = out[3 * c_lib + xyz].reshape(nb + nk)
+                    if sw_b:
+                        t = t.transpose(1, 0, 2, 3)
+                    if sw_k:
+                        t = t.transpose(0, 1, 3, 2)
+                    res[3 * c_user + xyz] = np.ascontiguousarray(t).ravel()
+            self._results = res
+            return res
         out = capi.eri_batch(self.ctx, bra, ket, np.array([[0, 0]], dtype=np.int32),
                              screening=int(scr), precision=self.precision, pure_out=True)[0]
         if bra.nprimpair == 0 or ket.nprimpair == 0:
@@ -135,9 +164,6 @@ class Engine:
             # (a set whose primitive *quartets* are all screened yields zeros here)
             self._results = [None]
             return None
-        n = [s1.size(), s2.size(), s3.size(), s4.size()]
-        nb = [n[1], n[0]] if sw_b else [n[0], n[1]]
-        nk = [n[3], n[2]] if sw_k else [n[2], n[3]]
         t = out.reshape(nb + nk)
         if sw_b:
             t = t.transpose(1, 0, 2, 3)

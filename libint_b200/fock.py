@@ -82,6 +82,32 @@ class FockBuilder:
         return self.fock.build(D, precision, use_schwarz=use_schwarz, rank=self.rank,
                                nranks=self.nranks, out=out, stats=stats)
 
+    def forces_2body(self, D, shell2atom=None, natoms=None, precision=1e-12, use_schwarz=True, stats=False):
+        """Two-body contribution to the forces, F2[natoms, 3] (hartree-fock++.cc:642-656: the trace of
+        compute_2body_fock_deriv<1> with D), summed over ranks.  shell2atom defaults to the map the
+        BasisSet was built with (BasisSet::shell2atom, basis.h.in)."""
+        if shell2atom is None:
+            shell2atom = self.obs.shell2atom
+        if natoms is None:
+            natoms = max(shell2atom) + 1
+        if min(shell2atom) < 0:
+            raise ValueError("forces_2body needs shell2atom (the basis was built from bare shells)")
+        if not isinstance(D, np.ndarray):
+            import torch
+            self.ctx.set_stream(torch.cuda.current_stream(torch.device("cuda", self.ctx.device)).cuda_stream)
+        out = self.fock.gradient(D, shell2atom, natoms, precision, use_schwarz=use_schwarz, rank=self.rank,
+                                 nranks=self.nranks, stats=stats)
+        g, st = out if stats else (out, None)
+        if self.nranks > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.as_tensor(g)
+            if dist.get_backend() == "nccl":
+                t = t.to(torch.device("cuda", self.ctx.device))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)   # 3 * natoms doubles
+            g = t.cpu().numpy()
+        return (g, st) if stats else g
+
     def __call__(self, D, precision=1e-12, use_schwarz=True):
         """Full G on every rank. With torch CUDA input the result is a torch CUDA tensor and the
         reduction is NCCL; with numpy input on one rank the result is numpy."""

@@ -17,6 +17,7 @@
 #define LIBINT2_REF_REALTYPE double
 #include <eri.h>  // /root/reference/src/bin/test_eri/eri.h
 
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -639,6 +640,158 @@ int lbo_basis_load(const char* name, int natom, const int* Z, const double* xyz_
     std::fprintf(stderr, "lbo_basis_load: %s\n", e.what());
     return -1;
   }
+}
+
+
+// ---- first geometric derivatives -------------------------------------------------------------------
+// The reference validates its generated derivative kernels against the closed-form eri() with a
+// derivative index (tests/eri/test.cc:381-445; eri.h:383-460: one 2*alpha*(a+1) - a*(a-1) step per
+// derivative).  The generated eri1 kernels cannot be built here, so that closed form IS the derivative
+// oracle: contracted CARTESIAN shell sets, out[d][n1*n2*n3*n4] for d = 3*centre + xyz, shells in the
+// order given (coefficients carry the normalization, coeff_is_raw as in make_shells).
+namespace {
+
+void deriv1_closed_set(const Shell& s0, const Shell& s1, const Shell& s2, const Shell& s3, double* out) {
+  const Shell* sh[4] = {&s0, &s1, &s2, &s3};
+  int l[4];
+  size_t nc[4];
+  for (int c = 0; c < 4; ++c) {
+    l[c] = sh[c]->contr[0].l;
+    nc[c] = (size_t)(l[c] + 1) * (l[c] + 2) / 2;
+  }
+  const size_t blk = nc[0] * nc[1] * nc[2] * nc[3];
+  std::fill(out, out + 12 * blk, 0.0);
+  // Cartesian components in the STANDARD order (cgshell_ordering.h)
+  std::vector<std::array<unsigned, 3>> q[4];
+  for (int c = 0; c < 4; ++c)
+    for (int x = l[c]; x >= 0; --x)
+      for (int y = l[c] - x; y >= 0; --y)
+        q[c].push_back({{(unsigned)x, (unsigned)y, (unsigned)(l[c] - x - y)}});
+  for (size_t p0 = 0; p0 < sh[0]->nprim(); ++p0)
+    for (size_t p1 = 0; p1 < sh[1]->nprim(); ++p1)
+      for (size_t p2 = 0; p2 < sh[2]->nprim(); ++p2)
+        for (size_t p3 = 0; p3 < sh[3]->nprim(); ++p3) {
+          const double c0123 = sh[0]->contr[0].coeff[p0] * sh[1]->contr[0].coeff[p1] *
+                               sh[2]->contr[0].coeff[p2] * sh[3]->contr[0].coeff[p3];
+          size_t e = 0;
+          for (auto& a : q[0])
+            for (auto& b : q[1])
+              for (auto& c : q[2])
+                for (auto& d : q[3]) {
+                  for (unsigned di = 0; di < 12; ++di) {
+                    unsigned idx[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    idx[di] = 1;
+                    out[di * blk + e] +=
+                        c0123 * eri(idx, a[0], a[1], a[2], sh[0]->alpha[p0], sh[0]->O.data(), b[0], b[1], b[2],
+                                    sh[1]->alpha[p1], sh[1]->O.data(), c[0], c[1], c[2], sh[2]->alpha[p2],
+                                    sh[2]->O.data(), d[0], d[1], d[2], sh[3]->alpha[p3], sh[3]->O.data(), 0);
+                  }
+                  ++e;
+                }
+        }
+}
+
+}  // namespace
+
+long lbo_deriv1_closed(const int* l, const int* nprim, const double* O, const double* alpha,
+                       const double* coeff, int coeff_is_raw, double* out, long out_cap) {
+  lbo_init();
+  const int pure[4] = {0, 0, 0, 0};
+  auto sh = make_shells(4, l, pure, nprim, O, alpha, coeff, coeff_is_raw);
+  long blk = 1;
+  for (auto& s : sh) blk *= (long)s.cartesian_size();
+  if (12 * blk > out_cap) return -2;
+  deriv1_closed_set(sh[0], sh[1], sh[2], sh[3], out);
+  return blk;
+}
+
+// Two-body forces exactly as the reference forms them: G1 = compute_2body_fock_deriv<1>
+// (hartree-fock++.cc:1775-2055: unique quartets s1 >= s2, s3 <= s1, s4 <= (s1 == s3 ? s2 : s3), degeneracy
+// weights, the six-fold digestion of every derivative shell set into G[3*atom + xyz], symmetrisation) and
+// F2(atom, xyz) = sum G1[i] o D (:648-656) -- with the closed-form derivative sets above in place of the
+// Engine, every pair significant, no screening.  CARTESIAN shells only (the caller back-transforms the
+// density of pure shells).  grad = 3 * natoms doubles.
+int lbo_fock_grad_closed(int nshell, const int* l, const int* nprim, const double* O, const double* alpha,
+                         const double* coeff, int coeff_is_raw, const double* D, int natoms,
+                         const int* shell2atom, int nthreads, double* grad) {
+  lbo_init();
+  std::vector<int> pure(nshell, 0);
+  auto obs = make_shells(nshell, l, pure.data(), nprim, O, alpha, coeff, coeff_is_raw);
+  std::vector<size_t> shell2bf(nshell);
+  size_t n = 0;
+  for (int s = 0; s < nshell; ++s) { shell2bf[s] = n; n += obs[s].size(); }
+  const int nthr = std::max(1, nthreads);
+  const size_t nderiv = 3 * (size_t)natoms;
+  std::vector<std::vector<double>> G(nthr, std::vector<double>(nderiv * n * n, 0.0));
+  parallel_do(nthr, [&](int tid) {
+    auto& g_all = G[tid];
+    std::vector<double> buf;
+    long s1234 = 0;
+    for (long s1 = 0; s1 != nshell; ++s1) {
+      const auto bf1_first = shell2bf[s1];
+      const auto n1 = obs[s1].size();
+      for (long s2 = 0; s2 <= s1; ++s2) {
+        const auto bf2_first = shell2bf[s2];
+        const auto n2 = obs[s2].size();
+        for (long s3 = 0; s3 <= s1; ++s3) {
+          const auto bf3_first = shell2bf[s3];
+          const auto n3 = obs[s3].size();
+          const long s4_max = (s1 == s3) ? s2 : s3;
+          for (long s4 = 0; s4 <= s4_max; ++s4) {
+            if ((s1234++) % nthr != tid) continue;
+            const auto bf4_first = shell2bf[s4];
+            const auto n4 = obs[s4].size();
+            const size_t n1234 = n1 * n2 * n3 * n4;
+            const double s12_deg = (s1 == s2) ? 1.0 : 2.0;
+            const double s34_deg = (s3 == s4) ? 1.0 : 2.0;
+            const double s12_34_deg = (s1 == s3) ? (s2 == s4 ? 1.0 : 2.0) : 2.0;
+            const double deg = s12_deg * s34_deg * s12_34_deg;
+            buf.resize(12 * n1234);
+            deriv1_closed_set(obs[s1], obs[s2], obs[s3], obs[s4], buf.data());
+            const int atoms4[4] = {shell2atom[s1], shell2atom[s2], shell2atom[s3], shell2atom[s4]};
+            for (int d = 0; d != 12; ++d) {
+              const size_t coord = (size_t)atoms4[d / 3] * 3 + d % 3;
+              double* g = g_all.data() + coord * n * n;
+              const double* shset = buf.data() + (size_t)d * n1234;
+              for (size_t f1 = 0, f1234 = 0; f1 != n1; ++f1) {
+                const auto bf1 = f1 + bf1_first;
+                for (size_t f2 = 0; f2 != n2; ++f2) {
+                  const auto bf2 = f2 + bf2_first;
+                  for (size_t f3 = 0; f3 != n3; ++f3) {
+                    const auto bf3 = f3 + bf3_first;
+                    for (size_t f4 = 0; f4 != n4; ++f4, ++f1234) {
+                      const auto bf4 = f4 + bf4_first;
+                      const double wv = shset[f1234] * deg;
+                      g[bf1 * n + bf2] += D[bf3 * n + bf4] * wv;
+                      g[bf3 * n + bf4] += D[bf1 * n + bf2] * wv;
+                      g[bf1 * n + bf3] -= 0.25 * D[bf2 * n + bf4] * wv;
+                      g[bf2 * n + bf4] -= 0.25 * D[bf1 * n + bf3] * wv;
+                      g[bf1 * n + bf4] -= 0.25 * D[bf2 * n + bf3] * wv;
+                      g[bf2 * n + bf3] -= 0.25 * D[bf1 * n + bf4] * wv;
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  });
+  for (size_t c = 0; c < nderiv; ++c) {
+    double f = 0.0;
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < n; ++j) {
+        double gij = 0.0, gji = 0.0;
+        for (int t = 0; t < nthr; ++t) {
+          gij += G[t][c * n * n + i * n + j];
+          gji += G[t][c * n * n + j * n + i];
+        }
+        f += 0.5 * (gij + gji) * D[i * n + j];   // GG = (G + G^T)/2 (:2044), then G1[i].cwiseProduct(D).sum()
+      }
+    grad[c] = f;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -106,6 +106,10 @@ def lib(fast=False, b200=False):
         L.lbo_compute_batch.restype = C.c_long
         L.lbo_basis_load.argtypes = [C.c_char_p, C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, ip, dp,
                                      dp, dp, ip]
+        if hasattr(L, "lbo_deriv1_closed"):
+            L.lbo_deriv1_closed.argtypes = [ip, ip, dp, dp, dp, C.c_int, dp, C.c_long]
+            L.lbo_deriv1_closed.restype = C.c_long
+            L.lbo_fock_grad_closed.argtypes = [C.c_int, ip, ip, dp, dp, dp, C.c_int, dp, C.c_int, ip, C.c_int, dp]
         L.lbo_init()
         _libs[path] = L
     return _libs[path]
@@ -314,6 +318,36 @@ def compute_batch(shells, quartets, nthreads=1, precision=0.0):
     if r != blk:
         raise RuntimeError("lbo_compute_batch failed (%d)" % r)
     return out
+
+
+def deriv1_closed(shells4):
+    """The twelve Cartesian derivative shell sets of one quartet from the reference's closed-form eri()
+    with a derivative index (tests/eri/test.cc:381-445) -> (12, n1*n2*n3*n4)."""
+    blk = 1
+    for i in range(4):
+        l = int(shells4.l[i])
+        blk *= (l + 1) * (l + 2) // 2
+    out = np.zeros((12, blk))
+    r = lib().lbo_deriv1_closed(_i(shells4.l), _i(shells4.nprim), _d(shells4.O), _d(shells4.alpha),
+                                _d(shells4.coeff), int(shells4.raw), _d(out), out.size)
+    if r != blk:
+        raise RuntimeError("lbo_deriv1_closed failed (%d)" % r)
+    return out
+
+
+def fock_grad_closed(shells, D, shell2atom, natoms, nthreads=1):
+    """F2[natoms, 3] as hartree-fock++.cc:648-656 forms it from compute_2body_fock_deriv<1>, with the
+    closed-form derivative sets; Cartesian shells only, no screening."""
+    assert not shells.pure.any(), "Cartesian shells only: back-transform the density of pure shells first"
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    s2a = np.ascontiguousarray(shell2atom, dtype=np.int32)
+    g = np.zeros((natoms, 3))
+    r = lib().lbo_fock_grad_closed(len(shells), _i(shells.l), _i(shells.nprim), _d(shells.O), _d(shells.alpha),
+                                   _d(shells.coeff), int(shells.raw), _d(D), int(natoms), _i(s2a), int(nthreads),
+                                   _d(g))
+    if r != 0:
+        raise RuntimeError("lbo_fock_grad_closed failed (%d)" % r)
+    return g
 
 
 def truth_batch(shells, quartets, nthreads=1, quad=False, with_lo=True):

@@ -6,8 +6,10 @@ reference's own Engine / ShellPair / FmEval_Chebyshev7 / eri() compiled where th
 
     python tests/golden/make_golden.py
 
+    python tests/golden/make_golden.py grad_h2o      # one file only
+
 Outputs (small, committed): tests/golden/eri_classes.npz, eri3_classes.npz, boys.npz,
-fock_h2o.npz, closed_form.npz.  The GPU box has no reference tree; there the parity tests
+fock_h2o.npz, closed_form.npz, grad_h2o.npz.  The GPU box has no reference tree; there the parity tests
 compare the CUDA path against these files and against the prebuilt oracle library.
 """
 import os
@@ -121,9 +123,48 @@ def fock_h2o():
     print("fock_h2o.npz done")
 
 
+def cartesianized(bs, D):
+    """(Cartesian twin of the basis as oracle shells, C^T D C): the density of a basis with pure shells in
+    the Cartesian functions of every shell, C = solid-harmonic coefficients (solidharmonics.h:114-174)"""
+    from util import _sph_matrix
+    blocks = []
+    for s in bs:
+        blocks.append(_sph_matrix(po, s.l) if s.pure else np.eye(nc(s.l)))
+    nbf = sum(b.shape[0] for b in blocks)
+    ncf = sum(b.shape[1] for b in blocks)
+    Cm = np.zeros((nbf, ncf))
+    r = c = 0
+    for b in blocks:
+        Cm[r:r + b.shape[0], c:c + b.shape[1]] = b
+        r += b.shape[0]
+        c += b.shape[1]
+    l, pure, nprim, O, al, co = bs.flat()
+    return po.Shells(l, np.zeros_like(pure), nprim, O, al, co, raw=False), Cm.T @ D @ Cm
+
+
+def grad_h2o():
+    """Two-body forces F2 of hartree-fock++.cc:642-656 (compute_2body_fock_deriv<1> traced with D) for H2O
+    and a seeded symmetric D, from the reference's closed-form derivative integrals (oracle
+    lbo_fock_grad_closed); no screening."""
+    from libint_b200.basis import BasisSet, H2O_XYZ_ANGSTROM, atoms_from_tuples
+    out = {}
+    for name in ("sto-3g", "6-31g*", "cc-pvdz"):
+        atoms = atoms_from_tuples(H2O_XYZ_ANGSTROM)
+        bs = BasisSet(name, atoms)
+        rng = np.random.default_rng(23)
+        D = rng.standard_normal((bs.nbf, bs.nbf)) * 0.2
+        D = 0.5 * (D + D.T)
+        sh, Dc = cartesianized(bs, D)
+        g = po.fock_grad_closed(sh, Dc, bs.shell2atom, len(atoms), nthreads=os.cpu_count() or 4)
+        tag = name.replace("-", "").replace("*", "s")
+        out[tag + "_D"] = D
+        out[tag + "_F2"] = g
+        print(name, g)
+    np.savez_compressed(os.path.join(HERE, "grad_h2o.npz"), **out)
+    print("grad_h2o.npz done")
+
+
 if __name__ == "__main__":
-    eri_classes()
-    eri3_classes()
-    boys()
-    closed_form()
-    fock_h2o()
+    which = sys.argv[1:] or ["eri_classes", "eri3_classes", "boys", "closed_form", "fock_h2o", "grad_h2o"]
+    for name in which:
+        globals()[name]()

@@ -121,7 +121,10 @@ def test_engine_argument_errors():
     with pytest.raises(E.lmax_exceeded):
         E.Engine(E.Operator.coulomb, 1, 7, ctx=object())
     with pytest.raises(NotImplementedError):
-        E.Engine(E.Operator.coulomb, 1, 1, deriv_order=1, ctx=object())
+        E.Engine(E.Operator.coulomb, 1, 1, deriv_order=2, ctx=object())
+    with pytest.raises(NotImplementedError):   # first derivatives: four-centre integrals only
+        E.Engine(E.Operator.coulomb, 1, 1, deriv_order=1, braket=E.BraKet.xs_xx, ctx=object())
+    assert len(E.Engine(E.Operator.coulomb, 1, 1, deriv_order=1, ctx=object()).results()) == 12
 
 
 def test_iface_library_exports_the_reference_boundary():
