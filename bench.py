@@ -191,6 +191,9 @@ def main():
     ap.add_argument("--fock-precision", type=float, default=1e-10)
     ap.add_argument("--fock256", choices=["auto", "on", "off"], default="auto",
                     help="configs[4], (H2O)_256 / cc-pVTZ: auto = when running on >= 2 GPUs")
+    ap.add_argument("--no-grad", action="store_true")
+    ap.add_argument("--grad-waters", default="3,3,3")
+    ap.add_argument("--grad-basis", default="cc-pvdz")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-df3c", action="store_true")
     ap.add_argument("--df3c-carbons", type=int, default=40)
@@ -392,6 +395,14 @@ def main():
         except capi.Lb200Error as e:
             df3c = {"error": str(e)}
 
+    # ---- two-body forces (first derivatives) of a water cluster -------------------------
+    grad = None
+    if not args.no_grad:
+        try:
+            grad = run_grad(args, ctx, dev, stream, rank, world, barrier, max_over_ranks)
+        except capi.Lb200Error as e:
+            grad = {"error": str(e)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -401,7 +412,7 @@ def main():
                        "l2_policy": "outputs (%.1f GB per class) exceed L2; pair tables are L2-resident by design"
                                     % (8 * max_blk * chunk / 1e9)},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "per_class": per, "fock": fock, "fock256": fock256, "df3c": df3c,
+            "per_class": per, "fock": fock, "fock256": fock256, "df3c": df3c, "grad": grad,
             # the strong-scaled half of the metric as top-level numbers: seconds per Fock build at this N
             "fock_build_seconds": fock.get("seconds") if isinstance(fock, dict) else None,
             "fock256_build_seconds": fock256.get("seconds") if isinstance(fock256, dict) else None}
@@ -602,6 +613,45 @@ def fock_roofline(f, fp64_peak, build_seconds, pure_basis=True):
             "note": "achieved/frac: this rank's model flops over the timed (unprofiled) build; per-class rows from "
                     "a separate profiled build (one stream sync per launch)",
             "classes": len(out), "top_classes": out[:12], "all_classes": out}
+
+
+def run_grad(args, ctx, dev, stream, rank, world, barrier, max_over_ranks):
+    """Two-body forces F2 (compute_2body_fock_deriv<1> traced with D, hartree-fock++.cc:642-656,1775-2055) of a
+    water cluster, quartets sharded over the ranks like the Fock build, 3 * natoms partial sums all-reduced."""
+    import torch
+    from libint_b200.basis import BasisSet, water_cluster
+    from libint_b200.fock import FockBuilder
+    nx, ny, nz = [int(x) for x in args.grad_waters.split(",")]
+    atoms = water_cluster(nx, ny, nz)
+    obs = BasisSet(args.grad_basis, atoms)
+    fb = FockBuilder(obs, ctx=ctx, rank=rank, nranks=world)
+    n = obs.nbf
+    rng = np.random.default_rng(7)
+    C = rng.standard_normal((n, max(1, n // 8))) / np.sqrt(n)
+    Dd = torch.from_numpy(C @ C.T).to(dev)
+    with torch.cuda.stream(stream):
+        fb.forces_2body(Dd, precision=args.fock_precision)   # warm-up (builds the shifted pair-block twins)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        g, st = fb.forces_2body(Dd, precision=args.fock_precision, stats=True)
+    barrier()
+    sec = max_over_ranks(time.perf_counter() - t0)
+    nq = st["nquartets"]
+    if world > 1:
+        t = torch.tensor([nq], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t)
+        nq = float(t.item())
+    return {"workload": "(H2O)_%d / %s two-body forces, Schwarz x density screened at %g"
+                        % (nx * ny * nz, args.grad_basis, args.fock_precision),
+            "nbf": n, "natoms": len(atoms), "shell_quartets": nq, "seconds": sec,
+            "derivative_shell_sets_per_s": 12 * nq / sec, "device_ms_this_rank": st["ms"],
+            "launches_this_rank": st["launches"], "n_gpus": world, "scaling": "strong",
+            "max_net_force": float(np.abs(g.sum(axis=0)).max()), "checksum": float(np.abs(g).sum()),
+            "cpu_baseline": None,
+            "note": "six shifted-class store launches + one contraction per (bra class, ket class) chunk; no CPU "
+                    "baseline: the reference's eri1 kernels are generated code that cannot be built here, and the "
+                    "closed-form derivative oracle is a checker, not an implementation to time"}
 
 
 def run_fock(args, ctx, dev, stream, rank, world, barrier, max_over_ranks, allreduce_sum_, fp64_peak=None,

@@ -5,9 +5,10 @@
 mirrors `hartree-fock++ [geometry.xyz] [basis]` (tests/hartree-fock/hartree-fock++.cc:233-244:
 default geometry h2o.xyz, default basis aug-cc-pVDZ) and prints the lines the reference's
 validation scripts parse (`** Hartree-Fock energy = ...`, hartree-fock++-validate.py:60-70,
-hartree-fock-validate.py:19-24), so those scripts can be pointed at this driver unchanged.
-The two-electron part of every Fock matrix comes from the CUDA path (lb200_fock_build);
-`--codata2010` converts Angstrom with the constant the plain `hartree-fock` test uses
+hartree-fock-validate.py:19-24; `** 1-body forces = ...` to `** Hartree-Fock forces = ...`,
+hartree-fock++-validate.py:128-132), so those scripts can be pointed at this driver unchanged.
+The two-electron part of every Fock matrix comes from the CUDA path (lb200_fock_build), the two-body
+forces from lb200_fock_grad; `--codata2010` converts Angstrom with the constant the plain `hartree-fock` test uses
 (hartree-fock.cc:306) instead of libint2's CODATA-2018 default.
 """
 import argparse
@@ -18,7 +19,8 @@ import numpy as np
 
 from . import basis as B
 from .fock import FockBuilder
-from .scf import RHF
+from . import capi
+from .scf import RHF, hf_forces
 
 
 def main(argv=None):
@@ -27,6 +29,7 @@ def main(argv=None):
     ap.add_argument("basis", nargs="?", default="aug-cc-pVDZ")
     ap.add_argument("--codata2010", action="store_true")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--no-forces", action="store_true")
     args = ap.parse_args(argv)
     b2a = B.BOHR_TO_ANGSTROM_CODATA2010 if args.codata2010 else B.BOHR_TO_ANGSTROM
     if args.geometry is None:
@@ -48,6 +51,17 @@ def main(argv=None):
         print(" %02d %20.12f %20.12e %20.12e" % (it, etot, ediff, rms))
     print("SCF wall time %.3f s, %s" % (time.time() - t0, "converged" if scf.converged else "NOT converged"))
     print("** Hartree-Fock energy = %20.12f" % e)
+    # forces, in the reference's output format (hartree-fock++.cc:613-716; parsed by
+    # hartree-fock++-validate.py:128-132).  A basis whose raised derivative classes have no kernel
+    # (f shells next to p/d shells) skips them, like a reference library built with LIBINT2_DERIV_ERI_ORDER 0.
+    if not args.no_forces:
+        try:
+            f = hf_forces(scf, fb)
+        except capi.Lb200Error as err:
+            print("forces skipped: %s" % err)
+        else:
+            for key in ("1-body", "Pulay", "2-body", "nuclear repulsion", "Hartree-Fock"):
+                print("** %s forces = %s " % (key, " ".join("%.15g" % x for x in f[key].ravel())))
     return 0 if scf.converged else 1
 
 

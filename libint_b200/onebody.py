@@ -104,13 +104,13 @@ def cart_to_pure(l):
     return M
 
 
-def _shell_pair_blocks(sa, sb, charges):
-    """Cartesian S, T, V blocks of one shell pair (contracted)."""
+def _shell_pair_blocks(sa, sb, charges, per_charge=False):
+    """Cartesian S, T, V blocks of one shell pair (contracted); per_charge: V as one block per charge."""
     la, lb = sa.l, sb.l
     ca, cb = _cart(la), _cart(lb)
     S = np.zeros((len(ca), len(cb)))
     T = np.zeros_like(S)
-    V = np.zeros_like(S)
+    V = np.zeros((len(charges),) + S.shape) if per_charge else np.zeros_like(S)
     A, B = np.asarray(sa.O, float), np.asarray(sb.O, float)
     AB = A - B
     for a, wa in zip(sa.alpha, sa.coeff):
@@ -141,10 +141,14 @@ def _shell_pair_blocks(sa, sb, charges):
                     ey = E[1][ay, by, :ay + by + 1]
                     ez = E[2][az, bz, :az + bz + 1]
                     v = 0.0
-                    for f, R in Rs:
-                        v += f * np.einsum("t,u,v,tuv->", ex, ey, ez,
+                    for k, (f, R) in enumerate(Rs):
+                        vk = f * np.einsum("t,u,v,tuv->", ex, ey, ez,
                                            R[:ax + bx + 1, :ay + by + 1, :az + bz + 1])
-                    V[ia, ib] += pref * v
+                        if per_charge:
+                            V[k, ia, ib] += pref * vk
+                        v += vk
+                    if not per_charge:
+                        V[ia, ib] += pref * v
     return S, T, V
 
 
@@ -182,3 +186,107 @@ def nuclear_repulsion(atoms):
         for b in atoms[:i]:
             e += a.atomic_number * b.atomic_number / float(np.linalg.norm(np.asarray(a.xyz) - np.asarray(b.xyz)))
     return e
+
+
+# ---------------------------------------------------------------------------------------------------
+# first derivatives of S, T, V (host numpy, like the integrals above: NOT the GPU hot path).  They close
+# the force expression of the reference's driver around the GPU two-body gradient:
+# compute_1body_ints_deriv<overlap|kinetic|nuclear>(1, obs, atoms), hartree-fock++.cc:1154-1228, used at
+# :601-627.  d/dA_x (a|O|b) = 2 alpha (a+1_x|O|b) - a_x (a-1_x|O|b); the derivative with respect to a
+# nuclear position follows from translational invariance of every single-charge term.
+# ---------------------------------------------------------------------------------------------------
+class _S:
+    def __init__(self, l, alpha, coeff, O):
+        self.l, self.alpha, self.coeff, self.O = l, alpha, coeff, O
+
+
+def _raised(sh):
+    return _S(sh.l + 1, sh.alpha, np.asarray(sh.coeff) * 2.0 * np.asarray(sh.alpha), sh.O)
+
+
+def _lowered(sh):
+    return _S(sh.l - 1, sh.alpha, sh.coeff, sh.O)
+
+
+def _deriv_first_index(up, dn, l):
+    """Cartesian derivative blocks d/dA_x of the first index from the raised / lowered blocks
+    (arrays [..., ncart(l+1), nb] and [..., ncart(l-1), nb] or None) -> [3][..., ncart(l), nb]"""
+    c = _cart(l)
+    iu = {q: k for k, q in enumerate(_cart(l + 1))}
+    idn = {q: k for k, q in enumerate(_cart(l - 1))} if l > 0 else {}
+    out = []
+    for d in range(3):
+        rows = []
+        for q in c:
+            qu = list(q)
+            qu[d] += 1
+            v = up[..., iu[tuple(qu)], :].copy()
+            if q[d] > 0:
+                qd = list(q)
+                qd[d] -= 1
+                v -= q[d] * dn[..., idn[tuple(qd)], :]
+            rows.append(v)
+        out.append(np.stack(rows, axis=-2))
+    return out
+
+
+def compute_1body_ints_deriv(obs, atoms):
+    """-> (S1, T1, V1), each [3 * natoms, nbf, nbf]: first derivatives with respect to the nuclear
+    coordinates (basis-function centres and, for V, the point charges)."""
+    n = obs.nbf
+    na = len(atoms)
+    S1 = np.zeros((3 * na, n, n))
+    T1 = np.zeros((3 * na, n, n))
+    V1 = np.zeros((3 * na, n, n))
+    charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+    c2p = {}
+
+    def pure(M, sa, sb):
+        if sa.pure:
+            M = np.einsum("pc,...cb->...pb", c2p.setdefault(sa.l, cart_to_pure(sa.l)), M)
+        if sb.pure:
+            M = np.einsum("...ac,pc->...ap", M, c2p.setdefault(sb.l, cart_to_pure(sb.l)))
+        return M
+
+    def side(sa, sb):
+        """derivatives with respect to the centre of sa of the (sa|O|sb) blocks: dS[3], dT[3], dV[3][ncharge]"""
+        up = _shell_pair_blocks(_raised(sa), sb, charges, per_charge=True)
+        dn = _shell_pair_blocks(_lowered(sa), sb, charges, per_charge=True) if sa.l > 0 else (None, None, None)
+        return [_deriv_first_index(u, d, sa.l) for u, d in zip(up, dn)]
+
+    for i, sa in enumerate(obs):
+        for j in range(i + 1):
+            sb = obs[j]
+            dA = side(sa, sb)
+            dB = [[np.swapaxes(x, -1, -2) for x in blk] for blk in side(sb, sa)]
+            ai, aj = obs.shell2atom[i], obs.shell2atom[j]
+            bi, bj = obs.shell2bf[i], obs.shell2bf[j]
+
+            def add(dst, coord, M):
+                M = pure(M, sa, sb)
+                dst[coord, bi:bi + M.shape[0], bj:bj + M.shape[1]] += M
+                if i != j:
+                    dst[coord, bj:bj + M.shape[1], bi:bi + M.shape[0]] += M.T
+
+            for d in range(3):
+                add(S1, 3 * ai + d, dA[0][d])
+                add(S1, 3 * aj + d, dB[0][d])
+                add(T1, 3 * ai + d, dA[1][d])
+                add(T1, 3 * aj + d, dB[1][d])
+                add(V1, 3 * ai + d, dA[2][d].sum(axis=0))
+                add(V1, 3 * aj + d, dB[2][d].sum(axis=0))
+                for k in range(na):   # the operator's own centre: -(d/dA + d/dB) of that charge's term
+                    add(V1, 3 * k + d, -(dA[2][d][k] + dB[2][d][k]))
+    return S1, T1, V1
+
+
+def nuclear_repulsion_forces(atoms):
+    """hartree-fock++.cc:668-701."""
+    F = np.zeros((len(atoms), 3))
+    for i in range(1, len(atoms)):
+        for j in range(i):
+            r = np.asarray(atoms[i].xyz) - np.asarray(atoms[j].xyz)
+            f = -r * atoms[i].atomic_number * atoms[j].atomic_number / float(np.linalg.norm(r)) ** 3
+            F[i] += f
+            F[j] -= f
+    return F

@@ -229,3 +229,26 @@ class RHFDevice:
         self.converged = ediff_rel <= conv and rms <= conv
         self.energy = ehf + self.enuc
         return self.energy
+
+
+def hf_forces(scf, builder, precision=None, use_schwarz=False):
+    """The force block of the reference's driver (tests/hartree-fock/hartree-fock++.cc:596-716) for a
+    converged RHF / RHFDevice object: one-body, Pulay, two-body and nuclear-repulsion contributions and their
+    sum, each [natoms, 3].  The two-body part comes from the GPU (FockBuilder.forces_2body =
+    compute_2body_fock_deriv<1> traced with D); the one-body derivative integrals are host numpy
+    (onebody.compute_1body_ints_deriv), like the reference's Engine::compute1 set-up steps."""
+    to_np = (lambda x: x.detach().cpu().numpy()) if hasattr(scf.D, "detach") else np.asarray
+    D, C, ev = to_np(scf.D), to_np(scf.C), to_np(scf.evals)
+    obs, atoms = scf.obs, scf.atoms
+    na = len(atoms)
+    S1, T1, V1 = onebody.compute_1body_ints_deriv(obs, atoms)
+    F1 = 2.0 * np.einsum("kij,ij->k", T1 + V1, D).reshape(na, 3)                 # :601-612
+    Co = C[:, :scf.ndocc]
+    W = (Co * ev[:scf.ndocc]) @ Co.T                                              # :617-619
+    FP = -2.0 * np.einsum("kij,ij->k", S1, W).reshape(na, 3)                      # :620-627
+    if precision is None:
+        precision = np.finfo(float).eps      # compute_2body_fock_deriv's default, hartree-fock++.cc:158-162
+    # the reference calls compute_2body_fock_deriv<1>(obs, atoms, D) without a Schwarz matrix (:649): no screening
+    F2 = builder.forces_2body(D, precision=precision, use_schwarz=use_schwarz)   # :648-656
+    FN = onebody.nuclear_repulsion_forces(atoms)                                  # :668-701
+    return {"1-body": F1, "Pulay": FP, "2-body": F2, "nuclear repulsion": FN, "Hartree-Fock": F1 + FP + F2 + FN}

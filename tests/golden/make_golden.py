@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import pyoracle as po  # noqa: E402
-from util import all_classes, nc, random_shell_table  # noqa: E402
+from util import all_classes, cartesianized, nc, random_shell_table  # noqa: E402
 
 
 def eri_classes():
@@ -123,25 +123,6 @@ def fock_h2o():
     print("fock_h2o.npz done")
 
 
-def cartesianized(bs, D):
-    """(Cartesian twin of the basis as oracle shells, C^T D C): the density of a basis with pure shells in
-    the Cartesian functions of every shell, C = solid-harmonic coefficients (solidharmonics.h:114-174)"""
-    from util import _sph_matrix
-    blocks = []
-    for s in bs:
-        blocks.append(_sph_matrix(po, s.l) if s.pure else np.eye(nc(s.l)))
-    nbf = sum(b.shape[0] for b in blocks)
-    ncf = sum(b.shape[1] for b in blocks)
-    Cm = np.zeros((nbf, ncf))
-    r = c = 0
-    for b in blocks:
-        Cm[r:r + b.shape[0], c:c + b.shape[1]] = b
-        r += b.shape[0]
-        c += b.shape[1]
-    l, pure, nprim, O, al, co = bs.flat()
-    return po.Shells(l, np.zeros_like(pure), nprim, O, al, co, raw=False), Cm.T @ D @ Cm
-
-
 def grad_h2o():
     """Two-body forces F2 of hartree-fock++.cc:642-656 (compute_2body_fock_deriv<1> traced with D) for H2O
     and a seeded symmetric D, from the reference's closed-form derivative integrals (oracle
@@ -154,7 +135,7 @@ def grad_h2o():
         rng = np.random.default_rng(23)
         D = rng.standard_normal((bs.nbf, bs.nbf)) * 0.2
         D = 0.5 * (D + D.T)
-        sh, Dc = cartesianized(bs, D)
+        sh, Dc = cartesianized(po, bs, D)
         g = po.fock_grad_closed(sh, Dc, bs.shell2atom, len(atoms), nthreads=os.cpu_count() or 4)
         tag = name.replace("-", "").replace("*", "s")
         out[tag + "_D"] = D

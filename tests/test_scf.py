@@ -160,6 +160,79 @@ def test_hartree_fock_cli_output_is_parsed_by_the_reference_validators(tmp_path)
         found = [m for m in found if m]
         assert len(found) == 1
         assert abs(eref - float(found[0].group(1))) < tol
+        if "aug-cc-pVDZ" in argv:   # the force lines, hartree-fock++-validate.py:30-36 pattern, :128-132,:147-155
+            num = r"\s*([+-]?(?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?)"
+            for key, (ref, ftol) in REF_FORCES.items():
+                m = [re.match(r"\*\* %s forces =" % re.escape(key) + num * 9, ln) for ln in r.stdout.splitlines()]
+                m = [x for x in m if x]
+                assert len(m) == 1, key
+                assert max(abs(float(v) - x) for v, x in zip(m[0].groups(), ref)) < ftol, key
+
+
+# forces of the reference's own validation run (h2o_rotated.xyz, aug-cc-pVDZ):
+# tests/hartree-fock/hartree-fock++-validate.py:84-112, tolerances :89,:95,:101,:107,:112
+REF_FORCES = {
+    "1-body": ([-5.43569555903312, -1.88298017654395, -2.17427822361352, 3.47022732536532, -2.96798871167808,
+                2.59189820350226, 1.9654682336678, 4.85096888822203, -0.417619979888738], 1e-9),
+    "Pulay": ([0.355265310323155, 0.123067513529209, 0.142106124129298, -0.224258642015539, 0.180741977786854,
+               -0.164305035772324, -0.131006668307617, -0.303809491316068, 0.0221989116430271], 1e-9),
+    "2-body": ([2.95100851670393, 1.02225933689958, 1.18040340668181, -1.89116113654409, 1.64868682617684,
+                -1.42151545972338, -1.05984738015984, -2.67094616307642, 0.241112053041571], 1e-9),
+    "nuclear repulsion": ([2.01500148332517, 0.698016989289171, 0.806000593330069, -1.28187870168764,
+                           1.07670120707691, -0.951756216715147, -0.733122781637531, -1.77471819636609,
+                           0.145755623385078], 1e-10),
+    "Hartree-Fock": ([-0.114420248680859, -0.0396363368259882, -0.0457680994723476, 0.0729288451180514,
+                      -0.0618587006374771, 0.0543214912914121, 0.0414914035628126, 0.101495037463456,
+                      -0.00855339181906306], 1e-9),
+}
+
+
+def test_oracle_forces_match_the_reference_golden_values(oracle):
+    """CPU: pins the derivative oracle (closed-form derivative integrals digested as
+    compute_2body_fock_deriv<1> does, oracle lbo_fock_grad_closed) and the host one-body derivative integrals
+    against the reference's golden forces, with D from the oracle-driven SCF."""
+    import os
+    from libint_b200 import onebody
+    from libint_b200.basis import BasisSet
+    from libint_b200.scf import RHF
+    from util import cartesianized
+    atoms = _atoms("h2o_rotated")
+    bs = BasisSet("aug-cc-pvdz", atoms)
+    scf = RHF(bs, atoms, _oracle_builder(oracle, bs))
+    scf.run()
+    assert scf.converged
+    S1, T1, V1 = onebody.compute_1body_ints_deriv(bs, atoms)
+    Co = scf.C[:, :scf.ndocc]
+    W = (Co * scf.evals[:scf.ndocc]) @ Co.T
+    sh, Dc = cartesianized(oracle, bs, scf.D)
+    f = {"1-body": 2.0 * np.einsum("kij,ij->k", T1 + V1, scf.D),
+         "Pulay": -2.0 * np.einsum("kij,ij->k", S1, W),
+         "2-body": oracle.fock_grad_closed(sh, Dc, bs.shell2atom, len(atoms), nthreads=os.cpu_count() or 4).ravel(),
+         "nuclear repulsion": onebody.nuclear_repulsion_forces(atoms).ravel()}
+    f["Hartree-Fock"] = sum(f.values())
+    for key, (ref, tol) in REF_FORCES.items():
+        err = np.abs(f[key] - np.array(ref)).max()
+        assert err < tol, "%s forces: max deviation %.3g (tolerance %g)" % (key, err, tol)
+
+
+@pytest.mark.gpu
+def test_gpu_forces_match_the_reference_golden_values(ctx):
+    """The reference's golden forces of its hartree-fock++ validation run: the 2-body part is
+    compute_2body_fock_deriv<1> traced with D (hartree-fock++.cc:642-656) -- here lb200_fock_grad on the GPU --
+    and the total closes with the host one-body derivative integrals; tolerances are the validator's."""
+    from libint_b200.basis import BasisSet
+    from libint_b200.fock import FockBuilder
+    from libint_b200.scf import RHF, hf_forces
+    atoms = _atoms("h2o_rotated")
+    bs = BasisSet("aug-cc-pvdz", atoms)
+    fb = FockBuilder(bs, ctx=ctx, rank=0, nranks=1)
+    scf = RHF(bs, atoms, lambda D, prec: fb.build_partial(np.ascontiguousarray(D), prec))
+    e = scf.run()
+    assert scf.converged and abs(e - (-76.003354058439)) < ETOL
+    f = hf_forces(scf, fb)
+    for key, (ref, tol) in REF_FORCES.items():
+        err = np.abs(f[key].ravel() - np.array(ref)).max()
+        assert err < tol, "%s forces: max deviation %.3g (tolerance %g)" % (key, err, tol)
 
 
 def test_hartree_fock_cli_fails_loudly_without_gpu():

@@ -59,6 +59,20 @@ def _sph_matrix(po, l):
     return np.array(rows)
 
 
+def cartesianized(po, bs, D):
+    """(Cartesian twin of the BasisSet as oracle shells, C^T D C): the density of a basis with pure shells in
+    the Cartesian functions of every shell, C = solid-harmonic coefficients (solidharmonics.h:114-174)"""
+    blocks = [_sph_matrix(po, s.l) if s.pure else np.eye(nc(s.l)) for s in bs]
+    Cm = np.zeros((sum(b.shape[0] for b in blocks), sum(b.shape[1] for b in blocks)))
+    r = c = 0
+    for b in blocks:
+        Cm[r:r + b.shape[0], c:c + b.shape[1]] = b
+        r += b.shape[0]
+        c += b.shape[1]
+    l, pure, nprim, O, al, co = bs.flat()
+    return po.Shells(l, np.zeros_like(pure), nprim, O, al, co, raw=False), Cm.T @ D @ Cm
+
+
 def truth_for(po, shells, idx):
     """extended-precision value (hi, lo) of the shell set shells[idx] in the layout the Engine
     returns (pure where flagged): the arbiter of oracle/truth.cc, transformed in long double."""
