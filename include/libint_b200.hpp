@@ -270,6 +270,20 @@ class FockBuilder {
                   "lb200_fock_build");
     return G;
   }
+  /// Two-body forces F2[3 * atom + xyz] = sum_ij G1[3 atom + xyz]_ij D_ij with G1 = compute_2body_fock_deriv<1>
+  /// (hartree-fock++.cc:1775-2055, traced with D at :648-656); this rank's share.  shell2atom =
+  /// BasisSet::shell2atom(atoms).  Throws lmax_exceeded when a raised derivative class has no kernel.
+  std::vector<double> compute_2body_forces(const std::vector<double>& D, const std::vector<int>& shell2atom,
+                                           int natoms, double precision, bool use_schwarz = true) const {
+    if ((long long)D.size() != (long long)nbf_ * nbf_) throw std::invalid_argument("FockBuilder: D size");
+    if ((int)shell2atom.size() != lb200_basis_nshell(bs_)) throw std::invalid_argument("FockBuilder: shell2atom size");
+    std::vector<double> F2((size_t)3 * natoms);
+    const int rc = lb200_fock_grad(fock_, D.data(), 0, precision, use_schwarz ? 1 : 0, rank_, nranks_, natoms,
+                                   shell2atom.data(), F2.data(), nullptr);
+    if (rc == LB200_ERR_LMAX) throw lmax_exceeded("FockBuilder::compute_2body_forces", LB200_MAX_AM - 1, LB200_MAX_AM);
+    detail::check(ctx_, rc, "lb200_fock_grad");
+    return F2;
+  }
   /// the Schwarz matrix of compute_schwarz_ints (nshell x nshell)
   std::vector<double> schwarz() const {
     const int ns = lb200_basis_nshell(bs_);

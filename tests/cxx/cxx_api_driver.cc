@@ -3,6 +3,7 @@
 //   eri  i j k l ...   prints Engine::compute(shells[i], shells[j], shells[k], shells[l]) per quartet
 //   eri3 i k l ...     BraKet::xs_xx
 //   fock Dfile prec    prints compute_2body_fock(D)
+//   forces Dfile prec natoms a0 a1 ...   prints compute_2body_forces(D, shell2atom)
 // Exit code 3 = the library reported that no GPU is usable (there is no CPU fallback).
 #include <cstdio>
 #include <cstdlib>
@@ -70,6 +71,18 @@ int main(int argc, char** argv) {
       for (auto& x : D) is >> x;
       const auto G = fb.compute_2body_fock(D, std::atof(argv[4]));
       for (double g : G) std::printf("%.17g ", g);
+      std::printf("\n");
+    } else if (!std::strcmp(argv[2], "forces")) {
+      libint_b200::FockBuilder fb(shells);
+      const int n = fb.nbf();
+      std::vector<double> D((size_t)n * n);
+      std::ifstream is(argv[3]);
+      for (auto& x : D) is >> x;
+      const int natoms = std::atoi(argv[5]);
+      std::vector<int> s2a;
+      for (int a = 6; a < argc; ++a) s2a.push_back(std::atoi(argv[a]));
+      const auto F2 = fb.compute_2body_forces(D, s2a, natoms, std::atof(argv[4]), /*use_schwarz=*/false);
+      for (double g : F2) std::printf("%.17g ", g);
       std::printf("\n");
     } else if (!std::strcmp(argv[2], "lmax")) {
       try {

@@ -101,3 +101,20 @@ def test_cxx_fock_builder_vs_oracle(driver, oracle, tmp_path):
     s1, s2 = np.array([(a, b) for a in range(ns) for b in range(a + 1)], dtype=np.int32).T
     Gref, _ = po.Fock(po.Shells(*bs.flat(), raw=False), s1, s2, nthreads=2).build(D, 1e-13)
     assert_parity(G, Gref, "C++ FockBuilder", rtol=1e-12, atol=2e-14)
+
+
+@pytest.mark.gpu
+def test_cxx_forces_vs_golden(driver, tmp_path):
+    """FockBuilder::compute_2body_forces (lb200_fock_grad) from C++ against the committed oracle forces"""
+    from libint_b200.basis import BasisSet, H2O_XYZ_ANGSTROM, atoms_from_tuples
+    d = np.load(os.path.join(ROOT, "tests", "golden", "grad_h2o.npz"))
+    bs = BasisSet("6-31g*", atoms_from_tuples(H2O_XYZ_ANGSTROM))
+    p = str(tmp_path / "shells.txt")
+    _write_shells(p, bs.flat())
+    dp = str(tmp_path / "D.txt")
+    np.savetxt(dp, d["631gs_D"].ravel(), fmt="%.17g")
+    r = subprocess.run([driver, p, "forces", dp, "1e-16", "3"] + [str(a) for a in bs.shell2atom],
+                       capture_output=True, text=True, check=True)
+    F2 = np.array([float(x) for x in r.stdout.split()]).reshape(3, 3)
+    ref = d["631gs_F2"]
+    assert np.abs(F2 - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
