@@ -140,12 +140,50 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
                                                const double (&ce)[3], double* __restrict__ Xq,
                                                const RowMeta& rmeta, double* __restrict__ acc) {
   constexpr int NM = K::FMAX - F + 1;
+#ifndef LB200_X_XPREF
+#define LB200_X_XPREF 0
+#endif
+  // LB200_X_XPREF = 1: the cross terms of component j+1 are loaded before component j is computed;
+  // 2: all cross terms of the level first (experiments: shared-memory latency in front of the last FMA of
+  // every value is the largest stall of the d-class kernels, profiles/r02_ncu_full_2222.txt)
+  [[maybe_unused]] double xall[(LB200_X_XPREF == 2 && K::EMAX > 0) ? nc(F) * NM : 1];
+  if constexpr (LB200_X_XPREF == 2 && K::EMAX > 0) {
+    static_for<nc(F)>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      constexpr C3 q = cxyz(F, j);
+      constexpr int d = cdir(q);
+      constexpr int jm1 = cidx(cadd(q, d, -1));
+      static_for<NM>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        xall[j * NM + m] = Xq[K::xslot(F - 1, jm1, m + 1) * K::NECX + rmeta.rm[d]];
+      });
+    });
+  }
+  [[maybe_unused]] double xcur[NM], xnxt[NM];
+  if constexpr (LB200_X_XPREF == 1 && K::EMAX > 0) {
+    constexpr C3 q0 = cxyz(F, 0);
+    constexpr int d0 = cdir(q0);
+    constexpr int j0m1 = cidx(cadd(q0, d0, -1));
+    static_for<NM>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      xcur[m] = Xq[K::xslot(F - 1, j0m1, m + 1) * K::NECX + rmeta.rm[d0]];
+    });
+  }
   static_for<nc(F)>([&](auto jc) {
     constexpr int j = decltype(jc)::value;
     constexpr C3 q = cxyz(F, j);
     constexpr int d = cdir(q);
     constexpr int qd = cget(q, d);
     constexpr int jm1 = cidx(cadd(q, d, -1));
+    if constexpr (LB200_X_XPREF == 1 && K::EMAX > 0 && j + 1 < nc(F)) {
+      constexpr C3 qn = cxyz(F, j + 1);
+      constexpr int dn = cdir(qn);
+      constexpr int jn1 = cidx(cadd(qn, dn, -1));
+      static_for<NM>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        xnxt[m] = Xq[K::xslot(F - 1, jn1, m + 1) * K::NECX + rmeta.rm[dn]];
+      });
+    }
     static_for<NM>([&](auto mc) {
       constexpr int m = decltype(mc)::value;
       double v = QC[d] * p1.v[jm1 * (NM + 1) + m] + WQ[d] * p1.v[jm1 * (NM + 1) + m + 1];
@@ -153,8 +191,11 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
         constexpr int jm2 = cidx(cadd(q, d, -2));
         v += koo2e[qd - 1] * (p2.v[jm2 * (NM + 2) + m] - roe * p2.v[jm2 * (NM + 2) + m + 1]);
       }
-      if constexpr (K::EMAX > 0)
-        v += ce[d] * Xq[K::xslot(F - 1, jm1, m + 1) * K::NECX + rmeta.rm[d]];
+      if constexpr (K::EMAX > 0) {
+        if constexpr (LB200_X_XPREF == 2) v += ce[d] * xall[j * NM + m];
+        else if constexpr (LB200_X_XPREF == 1) v += ce[d] * xcur[m];
+        else v += ce[d] * Xq[K::xslot(F - 1, jm1, m + 1) * K::NECX + rmeta.rm[d]];
+      }
       out.v[j * NM + m] = v;
       if constexpr (F < K::FMAX && m >= 1 && K::EMAX > 0) {
         if (rmeta.row < K::NECX) Xq[K::xslot(F, j, m) * K::NECX + rmeta.row] = v;
@@ -164,6 +205,8 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
         else acc[nc_upto(F - 1) - K::F0 + j] = v;
       }
     });
+    if constexpr (LB200_X_XPREF == 1 && K::EMAX > 0 && j + 1 < nc(F))
+      static_for<NM>([&](auto mc) { xcur[decltype(mc)::value] = xnxt[decltype(mc)::value]; });
   });
 }
 

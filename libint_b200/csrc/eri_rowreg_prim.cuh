@@ -76,6 +76,10 @@ struct RRP : RRK<LA, LB, LC, LD> {
   static constexpr int MINB = THREADS == 256 ? cmax(1, MINB128 / 2) : MINB128;
 };
 
+#ifndef LB200_X_NOZERO
+#define LB200_X_NOZERO 0
+#endif
+
 template <int LA, int LB, int LC, int LD, bool TR, bool FOCK>
 __global__ void __launch_bounds__(RRP<LA, LB, LC, LD, TR, FOCK>::THREADS, RRP<LA, LB, LC, LD, TR, FOCK>::MINB)
 eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
@@ -257,6 +261,11 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
   Off ocur;
   double deg_cur = 1.0;
   {
+    if constexpr (LB200_X_NOZERO) {   // stale stage contents must be finite numbers
+      if (lane_on)
+        for (int k = rmeta.row; k < K::PIPE; k += NEC) Q[k] = 0.0;
+      sync();
+    }
     const Task tk0 = load_task(base);
     tk_next = load_task(base + stride);
     ocur = load_off(tk0.t);
@@ -388,7 +397,14 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     // ---- ket HRR in registers: (row 0|c d) from (row 0|f 0), hrr.h:324 ---------------------
     double H[K::NCD];
     rr_hrr_regs<LC, LD>(acc, CD, H);
-    if (!on) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
+#ifndef LB200_X_NOZERO
+#define LB200_X_NOZERO 0
+#endif
+    // LB200_X_NOZERO: a screened-out quartet has F_m = 0 (boys_finish) and finite prerequisites (the stages are
+    // zeroed once in the prologue), so every recurrence value is already an exact zero
+    if constexpr (!LB200_X_NOZERO) {
+      if (!on) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });
+    }
 
     const unsigned task = base + qg;
     const bool valid = lane_on && task < ntasks;
@@ -430,8 +446,16 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         double O[K::NAB];
         rr_hrr_regs<LA, LB>(colin, ABv, O);
         if constexpr (!TR && !FOCK) {
-          double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
-          static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
+#ifndef LB200_X_STOREPTR
+#define LB200_X_STOREPTR 0
+#endif
+          if constexpr (LB200_X_STOREPTR) {   // one address, 36 immediate offsets
+            double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD) + cd;
+            static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD] = O[decltype(ic)::value]; });
+          } else {
+            double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD);
+            static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD + cd] = O[decltype(ic)::value]; });
+          }
         } else {
           double* fin = Q2 + K::OFF_FIN;
           static_for<K::NAB>([&](auto ic) { fin[decltype(ic)::value * K::CS + cd] = O[decltype(ic)::value]; });
