@@ -141,11 +141,14 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
                                                const RowMeta& rmeta, double* __restrict__ acc) {
   constexpr int NM = K::FMAX - F + 1;
 #ifndef LB200_X_XPREF
-#define LB200_X_XPREF 0
+#define LB200_X_XPREF 1
 #endif
-  // LB200_X_XPREF = 1: the cross terms of component j+1 are loaded before component j is computed;
-  // 2: all cross terms of the level first (experiments: shared-memory latency in front of the last FMA of
-  // every value is the largest stall of the d-class kernels, profiles/r02_ncu_full_2222.txt)
+  // Shared-memory latency in front of the last FMA of every value is the largest stall of the d-class kernels
+  // (short scoreboard, profiles/r02_ncu_full_2222.txt).  LB200_X_XPREF = 1 (default): the cross terms of
+  // component j+1 are loaded before component j is computed; 2: all cross terms of the level first; 0: at
+  // use.  Measured per 2^20 (dd|dd) / (dp|dd) / (dp|dp) quartets: 3.89 / 1.91 / 1.21 ms (0) -> 3.81 / 1.83 /
+  // 1.19 (1), 3.80 / 1.84 / 1.20 (2); whole sweep with the H-zeroing change below 125.5 -> 121.9 ms, Fock
+  // build unchanged (profiles/r03_variants.txt).
   [[maybe_unused]] double xall[(LB200_X_XPREF == 2 && K::EMAX > 0) ? nc(F) * NM : 1];
   if constexpr (LB200_X_XPREF == 2 && K::EMAX > 0) {
     static_for<nc(F)>([&](auto jc) {

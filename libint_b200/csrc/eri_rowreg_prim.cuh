@@ -77,7 +77,7 @@ struct RRP : RRK<LA, LB, LC, LD> {
 };
 
 #ifndef LB200_X_NOZERO
-#define LB200_X_NOZERO 0
+#define LB200_X_NOZERO 1
 #endif
 
 template <int LA, int LB, int LC, int LD, bool TR, bool FOCK>
@@ -397,10 +397,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     // ---- ket HRR in registers: (row 0|c d) from (row 0|f 0), hrr.h:324 ---------------------
     double H[K::NCD];
     rr_hrr_regs<LC, LD>(acc, CD, H);
-#ifndef LB200_X_NOZERO
-#define LB200_X_NOZERO 0
-#endif
-    // LB200_X_NOZERO: a screened-out quartet has F_m = 0 (boys_finish) and finite prerequisites (the stages are
+    // LB200_X_NOZERO (default): a screened-out quartet has F_m = 0 (boys_finish) and finite prerequisites (the stages are
     // zeroed once in the prologue), so every recurrence value is already an exact zero
     if constexpr (!LB200_X_NOZERO) {
       if (!on) static_for<K::NCD>([&](auto ic) { H[decltype(ic)::value] = 0.0; });

@@ -210,7 +210,9 @@ def test_pair_records_built_on_device_match_host(ctx):
                 # P: (a1 A + a2 B) / gamma contracts into an FMA on the GPU -- a few ulp of the
                 # coordinate scale where the sum cancels; K, 1/gamma, nonsph: relative
                 np.testing.assert_allclose(rd[:, :3], rh[:, :3], rtol=4e-15, atol=4e-15)
-                np.testing.assert_allclose(rd[:, 3:6], rh[:, 3:6], rtol=4e-15, atol=1e-300)
+                # K = c exp(-rho |AB|^2) / gamma: the rounding of the exponent (|x| up to ~40) shows up |x| ulp large
+                np.testing.assert_allclose(rd[:, 3], rh[:, 3], rtol=1e-13, atol=1e-300)
+                np.testing.assert_allclose(rd[:, 4:6], rh[:, 4:6], rtol=4e-15, atol=1e-300)
                 # ln_scr = -rho |AB|^2 + ln c_a + ln c_b is a sum of O(1..10) terms that may cancel
                 np.testing.assert_allclose(rd[:, 6], rh[:, 6], rtol=4e-15, atol=1e-13)
             # and the integrals made from them
