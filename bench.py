@@ -400,8 +400,8 @@ def main():
     if not args.no_grad:
         try:
             grad = run_grad(args, ctx, dev, stream, rank, world, barrier, max_over_ranks)
-        except capi.Lb200Error as e:
-            grad = {"error": str(e)}
+        except Exception as e:   # a "next" row must never take the headline metric down with it
+            grad = {"error": "%s: %s" % (type(e).__name__, e)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

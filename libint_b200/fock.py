@@ -47,6 +47,20 @@ def allreduce_sum_(G):
     return G
 
 
+def allreduce_forces(g, device=None):
+    """Sum over ranks of the partial two-body forces (numpy [natoms, 3]); 3 * natoms doubles, so the plain
+    torch.distributed collective is used (NCCL needs the buffer on the rank's GPU, gloo takes it as it is)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return g
+    t = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64)).clone()
+    if dist.get_backend() == "nccl":
+        t = t.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
 def make_comm(ctx):
     """NCCL communicator of the C ABI (lb200_comm_create) for the ranks of the current
     torch.distributed job: rank 0's ncclUniqueId travels over the process group that torchrun set up
@@ -99,13 +113,7 @@ class FockBuilder:
                                  nranks=self.nranks, stats=stats)
         g, st = out if stats else (out, None)
         if self.nranks > 1:
-            import torch
-            import torch.distributed as dist
-            t = torch.as_tensor(g)
-            if dist.get_backend() == "nccl":
-                t = t.to(torch.device("cuda", self.ctx.device))
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)   # 3 * natoms doubles
-            g = t.cpu().numpy()
+            g = allreduce_forces(g, self.ctx.device)
         return (g, st) if stats else g
 
     def __call__(self, D, precision=1e-12, use_schwarz=True):

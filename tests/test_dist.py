@@ -32,6 +32,11 @@ def _worker(rank, world, port, q):
     Gpart, _ = f.build(D, 1e-12, task_stride=world, task_offset=rank)
     G = torch.from_numpy(Gpart.copy())
     fock.allreduce_sum_(G)
+    # the 3 * natoms partial forces go through the same process group (FockBuilder.forces_2body)
+    part = np.arange(9, dtype=np.float64).reshape(3, 3) * (rank + 1)
+    tot = fock.allreduce_forces(part)
+    assert np.array_equal(tot, np.arange(9, dtype=np.float64).reshape(3, 3) * sum(range(1, world + 1)))
+    assert np.array_equal(part, np.arange(9, dtype=np.float64).reshape(3, 3) * (rank + 1))   # input untouched
     if rank == 0:
         Gfull, _ = f.build(D, 1e-12)
         q.put(float(np.max(np.abs(G.numpy() - Gfull))))
