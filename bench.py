@@ -57,24 +57,36 @@ def class_table(cl, npairs, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started BEFORE the warm-up steps (nvidia-smi
+    needs several hundred ms to deliver its first sample; a three-step timed region is shorter than that), the
+    samples are then cut to the timed window by their timestamps; if the window is too short to hold one, the
+    samples of the warm-up steps -- the same kernels back to back -- are reported and `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.12)   # let the sample that covers the end of the window arrive
         self.p.terminate()
         try:
             self.p.wait(5)
@@ -82,23 +94,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, pw = [], [], set(), []
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.f.read().splitlines():
             t = [x.strip() for x in ln.split(",")]
-            if len(t) < 8:
+            if len(t) < 9:
                 continue
             try:
-                sm.append(float(t[0])); mx.append(float(t[1])); pw.append(float(t[2]))
+                ts = datetime.datetime.strptime(t[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(t[1]), float(t[2]), float(t[3]),
+                             [nm for nm, v in zip(names, t[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, t[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                   "reasons": sorted(reasons), "power_w_max": max(pw), "samples": len(sm)}
+        window = "timed region"
+        sel = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.06]
+        if not sel:   # region shorter than the sampling latency: the warm-up steps ran the same kernels
+            sel = [r for r in rows if self.t1 is None or r[0] <= self.t1 + 0.06]
+            window = "warm-up + timed region (timed region shorter than one sampling interval)"
+        if sel:
+            # under load = the GPU is drawing power for the kernels; idle samples before the first launch would
+            # drag the median to the idle clock
+            busy = [r for r in sel if r[3] >= 0.5 * max(x[3] for x in sel)] or sel
+            out = {"sm_mhz": float(np.median([r[1] for r in busy])), "sm_max_mhz": float(max(r[2] for r in sel)),
+                   "reasons": sorted({nm for r in sel for nm in r[4]}), "power_w_max": max(r[3] for r in sel),
+                   "samples": len(busy), "window": window}
         return out
 
 
@@ -269,10 +289,12 @@ def main():
 
     # timing rule: at least three untimed warm-up steps, whatever was asked for
     args.warmup = max(3, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         sweep_step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     l0 = ctx.launch_count
     ev_all = []
     t_start = torch.cuda.Event(enable_timing=True)
@@ -284,6 +306,8 @@ def main():
         ev_all.append(ev)
     t_end.record(stream)
     barrier()
+    if sampler:
+        sampler.mark_end()
     launches = ctx.launch_count - l0
     ms_total = max_over_ranks(t_start.elapsed_time(t_end))
     clocks = sampler.stop() if sampler else None
