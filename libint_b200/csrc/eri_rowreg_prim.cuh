@@ -79,6 +79,20 @@ struct RRP : RRK<LA, LB, LC, LD> {
 #ifndef LB200_X_NOZERO
 #define LB200_X_NOZERO 1
 #endif
+// timing decomposition only (results are WRONG when any of these is set): skip the global stores of the bra-HRR
+// lanes / the whole bra HRR / the register pyramid / the Boys evaluation
+#ifndef LB200_DIAG_NOSTORE
+#define LB200_DIAG_NOSTORE 0
+#endif
+#ifndef LB200_DIAG_NOBRAHRR
+#define LB200_DIAG_NOBRAHRR 0
+#endif
+#ifndef LB200_DIAG_NOVRR
+#define LB200_DIAG_NOVRR 0
+#endif
+#ifndef LB200_DIAG_NOBOYS
+#define LB200_DIAG_NOBOYS 0
+#endif
 
 template <int LA, int LB, int LC, int LD, bool TR, bool FOCK>
 __global__ void __launch_bounds__(RRP<LA, LB, LC, LD, TR, FOCK>::THREADS, RRP<LA, LB, LC, LD, TR, FOCK>::MINB)
@@ -363,7 +377,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -----------------------
     double* Xq = Q + K::OFF_X;
-    if constexpr (FMAX >= 1) {
+    if constexpr (FMAX >= 1 && !LB200_DIAG_NOVRR) {
       sync();
       Lvl<FMAX, 1> l1;
       rr_build_level<K, 1, false>(l1, l0, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
@@ -428,7 +442,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     const BoysState bn = boys_prepare(onext, SN, tk_next.lnp);
     const double touched = boys_touch(bn);
 
-    if constexpr (LB > 0) {
+    if constexpr (LB > 0 && !LB200_DIAG_NOBRAHRR) {
       // ---- bra HRR in registers: (a b|c d) from (e 0|c d), hrr.h:246 -----------------------
       for (int item = gl; item < QPG * K::NCD; item += GROUP) {
         const int q2 = item / K::NCD, cd = item - q2 * K::NCD;
@@ -446,7 +460,11 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 #ifndef LB200_X_STOREPTR
 #define LB200_X_STOREPTR 0
 #endif
-          if constexpr (LB200_X_STOREPTR) {   // one address, 36 immediate offsets
+          if constexpr (LB200_DIAG_NOSTORE) {
+            double t = 0.0;
+            static_for<K::NAB>([&](auto ic) { t += O[decltype(ic)::value]; });
+            if (t == 123.456) p.out[0] = t;
+          } else if constexpr (LB200_X_STOREPTR) {   // one address, 36 immediate offsets
             double* __restrict__ o = p.out + (size_t)(base + q2) * (K::NAB * K::NCD) + cd;
             static_for<K::NAB>([&](auto ic) { o[decltype(ic)::value * K::NCD] = O[decltype(ic)::value]; });
           } else {
@@ -492,7 +510,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       // keep the touch alive without changing any value: (touched != touched) is false for
       // every finite table entry
       if (touched != touched) b2.pfac = touched;
-      boys_finish(b2, SN);
+      if constexpr (!LB200_DIAG_NOBOYS) boys_finish(b2, SN);
     }
     ocur = onext;
     deg_cur = tk_next.deg;
