@@ -6,7 +6,9 @@
 //   Libint_t (include/libint2/util/generated/libint2_types.h),
 //   libint2_build_eri[la][lb][lc][ld], libint2_build_3eri[l][lc][ld], libint2_build_2eri[l1][l2],
 //   libint2_build_default, libint2_static_init/cleanup,
-//   libint2_{need_memory,init,cleanup}_{default,eri,3eri,2eri}.
+//   libint2_{need_memory,init,cleanup}_{default,eri,3eri,2eri},
+//   and for first derivatives libint2_build_eri1[la][lb][lc][ld] + libint2_{need_memory,init,cleanup}_eri1
+//   (LIBINT2_MAX_DERIV_ORDER 1: Engine(Operator::coulomb, max_nprim, max_l, 1), engine.impl.h:1704-1751).
 // so that the reference's unmodified header-only libint2::Engine (and any C caller that fills
 // Libint_t itself) links against this library instead of libint2.a.
 //
@@ -104,6 +106,118 @@ void build_any(const Libint_t* inteval, int la, int lb, int lc, int ld, int ncen
   inteval[0].targets[0] = inteval[0].stack;
 }
 
+// ---- first derivatives: libint2_build_eri1[la][lb][lc][ld] -------------------------------------------------
+// Twelve targets, index 3 * centre + xyz.  Same construction as lb200_eri_deriv1_batch (csrc/deriv.cu):
+// d/dA_x (ab|cd) = (a+1_x b|cd)[2 alpha_a] - a_x (a-1_x b|cd) from six ordinary shell sets with one angular
+// momentum shifted, the fourth centre by translational invariance.  The factor 2 alpha of the raised sets is what
+// Engine::compute2 stores per primitive in two_alpha{0,1}_{bra,ket} (engine.impl.h:1739-1750); it scales that
+// primitive's (ss|ss)^(m).  A pair whose second shell becomes the larger one is handed over swapped (PA -> PB,
+// AB -> BA; the members exist, engine.impl.h:1525,1567).
+struct Cart { int x, y, z; };
+inline Cart cart_of(int l, int i) {
+  int k = 0;
+  for (int x = l; x >= 0; --x)
+    for (int y = l - x; y >= 0; --y, ++k)
+      if (k == i) return Cart{x, y, l - x - y};
+  return Cart{0, 0, 0};
+}
+inline int cart_index(int x, int y, int z) {
+  const int l = x + y + z;
+  return ((l - x + 1) * (l - x)) / 2 + l - x - y;
+}
+
+void build_deriv_any(const Libint_t* inteval, int la, int lb, int lc, int ld) {
+  lb200_context* ctx = thread_context();
+  const int n = inteval[0].contrdepth;
+  const int l[4] = {la, lb, lc, ld};
+  const int nn[4] = {ncart(la), ncart(lb), ncart(lc), ncart(ld)};
+  const size_t blk = (size_t)nn[0] * nn[1] * nn[2] * nn[3];
+  static thread_local std::vector<double> sets[6];
+  std::vector<double>& r = tls.recs;
+  int stride[6][4];
+  for (int k = 0; k < 6; ++k) {
+    const int c = k / 2, sgn = (k & 1) ? -1 : +1;
+    sets[k].clear();
+    if (l[c] + sgn < 0) continue;
+    int m[4] = {l[0], l[1], l[2], l[3]};
+    m[c] += sgn;
+    const int Lk = m[0] + m[1] + m[2] + m[3];
+    const bool sw_bra = m[0] < m[1], sw_ket = m[2] < m[3];
+    r.assign((size_t)LB200_PREREQ_DOUBLES * (n > 0 ? n : 1), 0.0);
+    for (int i = 0; i < n; ++i) {
+      const Libint_t* p = inteval + i;
+      double* o = r.data() + (size_t)LB200_PREREQ_DOUBLES * i;
+      const double* F = fm_ptr(p);
+      double scale = 1.0;
+      if (sgn > 0)
+        scale = c == 0 ? p->two_alpha0_bra[0] : (c == 1 ? p->two_alpha0_ket[0] : p->two_alpha1_bra[0]);
+      for (int q = 0; q <= Lk; ++q) o[q] = F[q] * scale;
+      double* g = o + 25;
+      if (sw_bra) { g[0] = p->PB_x[0]; g[1] = p->PB_y[0]; g[2] = p->PB_z[0]; }
+      else { g[0] = p->PA_x[0]; g[1] = p->PA_y[0]; g[2] = p->PA_z[0]; }
+      if (sw_ket) { g[3] = p->QD_x[0]; g[4] = p->QD_y[0]; g[5] = p->QD_z[0]; }
+      else { g[3] = p->QC_x[0]; g[4] = p->QC_y[0]; g[5] = p->QC_z[0]; }
+      g[6] = p->WP_x[0]; g[7] = p->WP_y[0]; g[8] = p->WP_z[0];
+      g[9] = p->WQ_x[0]; g[10] = p->WQ_y[0]; g[11] = p->WQ_z[0];
+      g[12] = p->oo2z[0]; g[13] = p->oo2e[0]; g[14] = p->oo2ze[0]; g[15] = p->roz[0]; g[16] = p->roe[0];
+    }
+    const double sb = sw_bra ? -1.0 : 1.0, sk = sw_ket ? -1.0 : 1.0;
+    const double geom[6] = {sb * inteval[0].AB_x[0], sb * inteval[0].AB_y[0], sb * inteval[0].AB_z[0],
+                            sk * inteval[0].CD_x[0], sk * inteval[0].CD_y[0], sk * inteval[0].CD_z[0]};
+    const int pa = sw_bra ? m[1] : m[0], pb = sw_bra ? m[0] : m[1], pc = sw_ket ? m[3] : m[2], pd = sw_ket ? m[2] : m[3];
+    const int mm[4] = {ncart(m[0]), ncart(m[1]), ncart(m[2]), ncart(m[3])};
+    sets[k].assign((size_t)mm[0] * mm[1] * mm[2] * mm[3], 0.0);
+    const int off[2] = {0, n};
+    const int rc = lb200_eri_prereq_batch(ctx, pa, pb, pc, pd, 1, off, r.data(), geom, sets[k].data());
+    if (rc != LB200_OK) {
+      std::fprintf(stderr, "libint2 (B200): derivative build (%d %d|%d %d), shifted set %d failed (%d): %s\n", la, lb,
+                   lc, ld, k, rc, lb200_last_error(ctx));
+      std::abort();
+    }
+    // strides of the (a, b, c, d) component indices in the layout [pa][pb][pc][pd] just written
+    const int i0 = sw_bra ? 1 : 0, i1 = sw_bra ? 0 : 1, i2 = sw_ket ? 3 : 2, i3 = sw_ket ? 2 : 3;
+    stride[k][i3] = 1;
+    stride[k][i2] = mm[i3];
+    stride[k][i1] = mm[i2] * mm[i3];
+    stride[k][i0] = mm[i1] * mm[i2] * mm[i3];
+  }
+  double* out = inteval[0].stack;
+  for (int ia = 0, e = 0; ia < nn[0]; ++ia)
+    for (int ib = 0; ib < nn[1]; ++ib)
+      for (int ic = 0; ic < nn[2]; ++ic)
+        for (int id = 0; id < nn[3]; ++id, ++e) {
+          const int idx[4] = {ia, ib, ic, id};
+          double dsum[3] = {0, 0, 0};
+          for (int c = 0; c < 3; ++c) {
+            const Cart q = cart_of(l[c], idx[c]);
+            const int qv[3] = {q.x, q.y, q.z};
+            size_t rest_p = 0, rest_m = 0;
+            for (int x = 0; x < 4; ++x)
+              if (x != c) {
+                rest_p += (size_t)idx[x] * stride[2 * c][x];
+                if (l[c] > 0) rest_m += (size_t)idx[x] * stride[2 * c + 1][x];
+              }
+            for (int d = 0; d < 3; ++d) {
+              int up[3] = {q.x, q.y, q.z};
+              ++up[d];
+              double v = sets[2 * c][rest_p + (size_t)cart_index(up[0], up[1], up[2]) * stride[2 * c][c]];
+              if (qv[d] > 0) {
+                int dn[3] = {q.x, q.y, q.z};
+                --dn[d];
+                v -= qv[d] * sets[2 * c + 1][rest_m + (size_t)cart_index(dn[0], dn[1], dn[2]) * stride[2 * c + 1][c]];
+              }
+              out[(size_t)(3 * c + d) * blk + e] = v;
+              dsum[d] += v;
+            }
+          }
+          for (int d = 0; d < 3; ++d) out[(size_t)(9 + d) * blk + e] = -dsum[d];   // translational invariance
+        }
+  for (int s = 0; s < 12; ++s) inteval[0].targets[s] = out + (size_t)s * blk;
+}
+
+template <int la, int lb, int lc, int ld>
+void build4d(const Libint_t* p) { build_deriv_any(p, la, lb, lc, ld); }
+
 constexpr int N4 = LIBINT2_MAX_AM_eri + 1, N3 = LIBINT2_MAX_AM_3eri + 1, N2 = LIBINT2_MAX_AM_2eri + 1;
 
 template <int la, int lb, int lc, int ld>
@@ -136,6 +250,7 @@ void (*libint2_build_default[LIBINT2_MAX_AM_default + 1][LIBINT2_MAX_AM_default 
 void (*libint2_build_eri[N4][N4][N4][N4])(const Libint_t*);
 void (*libint2_build_3eri[N3][N3][N3])(const Libint_t*);
 void (*libint2_build_2eri[N2][N2])(const Libint_t*);
+void (*libint2_build_eri1[LIBINT2_MAX_AM_eri1 + 1][LIBINT2_MAX_AM_eri1 + 1][LIBINT2_MAX_AM_eri1 + 1][LIBINT2_MAX_AM_eri1 + 1])(const Libint_t*);
 
 }
 
@@ -164,6 +279,18 @@ void fill2_one() {
     if (lb200_eri_class_supported(l1, 0, l2, 0)) libint2_build_2eri[l1][l2] = &build2<l1, l2>;
   }
 }
+constexpr int N4D = LIBINT2_MAX_AM_eri1 + 1;
+template <int I>
+void fill4d_one() {
+  constexpr int la = I / (N4D * N4D * N4D), lb = (I / (N4D * N4D)) % N4D, lc = (I / N4D) % N4D, ld = I % N4D;
+  // same canonical rule; (ss|ss) included: its derivatives are (ps|ss)-type sets (tests/eri/test.cc:238-249)
+  if constexpr (la >= lb && lc >= ld && la + lb <= lc + ld) {
+    long long plan[30];
+    if (lb200_eri_deriv1_plan(la, lb, lc, ld, plan) == LB200_OK) libint2_build_eri1[la][lb][lc][ld] = &build4d<la, lb, lc, ld>;
+  }
+}
+template <int... I>
+void fill4d(std::integer_sequence<int, I...>) { (fill4d_one<I>(), ...); }
 template <int... I>
 void fill4(std::integer_sequence<int, I...>) { (fill4_one<I>(), ...); }
 template <int... I>
@@ -183,6 +310,8 @@ void libint2_static_init() {
   fill4(std::make_integer_sequence<int, N4 * N4 * N4 * N4>{});
   fill3(std::make_integer_sequence<int, N3 * N3 * N3>{});
   fill2(std::make_integer_sequence<int, N2 * N2>{});
+  std::memset(libint2_build_eri1, 0, sizeof(libint2_build_eri1));
+  fill4d(std::make_integer_sequence<int, N4D * N4D * N4D * N4D>{});
 }
 
 void libint2_static_cleanup() {
@@ -206,6 +335,17 @@ void libint2_cleanup_default(Libint_t* e) {   // iface.cc:395-413
   e[0].vstack = nullptr;
 }
 void libint2_cleanup_eri(Libint_t* e) { libint2_cleanup_default(e); }
+size_t libint2_need_memory_eri1(int max_am) { return 12 * need_memory(max_am); }
+void libint2_init_eri1(Libint_t* e, int max_am, void* buf) {
+  double* stack = buf ? static_cast<double*>(buf)
+                      : static_cast<double*>(std::malloc(libint2_need_memory_eri1(max_am) * sizeof(double)));
+  e[0].stack = stack;
+  e[0].vstack = stack;
+  for (int s = 0; s < 12; ++s) e[0].targets[s] = nullptr;
+  e[0].veclen = 1;
+  e[0].contrdepth = 0;
+}
+void libint2_cleanup_eri1(Libint_t* e) { libint2_cleanup_default(e); }
 void libint2_cleanup_3eri(Libint_t* e) { libint2_cleanup_default(e); }
 void libint2_cleanup_2eri(Libint_t* e) { libint2_cleanup_default(e); }
 

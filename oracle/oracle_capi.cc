@@ -643,6 +643,41 @@ int lbo_basis_load(const char* name, int natom, const int* Z, const double* xyz_
 }
 
 
+// Engine(Operator::coulomb, max_nprim, max_l, deriv_order = 1).compute2<coulomb, xx_xx, 1>: the twelve shell
+// sets results()[0..11] (3 * centre + xyz, caller's shell order, pure where flagged) of one quartet.  Only in a
+// build whose generated headers provide derivative order 1 -- i.e. librefengine_b200.so, the reference Engine
+// on the GPU library's Libint_t boundary; the oracle's own shim headers stop at order 0 (returns -3 there).
+long lbo_compute2_deriv1(const int* l, const int* pure, const int* nprim, const double* O, const double* alpha,
+                         const double* coeff, int coeff_is_raw, double precision, double* out, long out_cap) {
+#if LIBINT2_MAX_DERIV_ORDER >= 1
+  lbo_init();
+  auto sh = make_shells(4, l, pure, nprim, O, alpha, coeff, coeff_is_raw);
+  int max_nprim = 0, max_l = 0;
+  for (auto& s : sh) {
+    max_nprim = std::max<int>(max_nprim, s.nprim());
+    max_l = std::max<int>(max_l, s.contr[0].l);
+  }
+  try {
+    Engine engine(Operator::coulomb, max_nprim, max_l, 1, precision);
+    const auto& buf = engine.results();
+    size_t n = 1;
+    for (auto& s : sh) n *= s.size();
+    engine.compute2<Operator::coulomb, BraKet::xx_xx, 1>(sh[0], sh[1], sh[2], sh[3]);
+    if (buf[0] == nullptr) return 0;
+    if ((long)(12 * n) > out_cap) return -2;
+    for (int d = 0; d < 12; ++d) std::memcpy(out + d * n, buf[d], n * sizeof(double));
+    return (long)n;
+  } catch (std::exception& e) {
+    std::fprintf(stderr, "lbo_compute2_deriv1: %s\n", e.what());
+    return -1;
+  }
+#else
+  (void)l; (void)pure; (void)nprim; (void)O; (void)alpha; (void)coeff; (void)coeff_is_raw; (void)precision;
+  (void)out; (void)out_cap;
+  return -3;
+#endif
+}
+
 // ---- first geometric derivatives -------------------------------------------------------------------
 // The reference validates its generated derivative kernels against the closed-form eri() with a
 // derivative index (tests/eri/test.cc:381-445; eri.h:383-460: one 2*alpha*(a+1) - a*(a-1) step per

@@ -106,6 +106,9 @@ def lib(fast=False, b200=False):
         L.lbo_compute_batch.restype = C.c_long
         L.lbo_basis_load.argtypes = [C.c_char_p, C.c_int, ip, dp, C.c_int, C.c_int, ip, ip, ip, dp,
                                      dp, dp, ip]
+        if hasattr(L, "lbo_compute2_deriv1"):
+            L.lbo_compute2_deriv1.argtypes = [ip, ip, ip, dp, dp, dp, C.c_int, C.c_double, dp, C.c_long]
+            L.lbo_compute2_deriv1.restype = C.c_long
         if hasattr(L, "lbo_deriv1_closed"):
             L.lbo_deriv1_closed.argtypes = [ip, ip, dp, dp, dp, C.c_int, dp, C.c_long]
             L.lbo_deriv1_closed.restype = C.c_long
@@ -318,6 +321,22 @@ def compute_batch(shells, quartets, nthreads=1, precision=0.0):
     if r != blk:
         raise RuntimeError("lbo_compute_batch failed (%d)" % r)
     return out
+
+
+def compute2_deriv1(shells4, precision=0.0, b200=True):
+    """The reference's unmodified Engine with deriv_order = 1 on one quartet -> (12, n1*n2*n3*n4), or None when
+    screened out.  b200=True (the only build whose headers have derivative order 1): the Engine runs on the GPU
+    library's Libint_t boundary (libint2_build_eri1 of liblibint_b200_iface.so)."""
+    n = 1
+    for i in range(4):
+        n *= shells4.size(i)
+    out = np.zeros((12, n))
+    r = lib(b200=b200).lbo_compute2_deriv1(*shells4.args(), float(precision), _d(out), out.size)
+    if r == -3:
+        raise RuntimeError("this oracle build has LIBINT2_MAX_DERIV_ORDER 0")
+    if r < 0:
+        raise RuntimeError("lbo_compute2_deriv1 failed (%d)" % r)
+    return None if r == 0 else out
 
 
 def deriv1_closed(shells4):

@@ -88,6 +88,38 @@ def test_reference_engine_pure_3center_2center(oracle):
     np.testing.assert_allclose(oracle.compute2(s0, b200=True), oracle.compute2(s0), rtol=1e-13)
 
 
+def test_reference_engine_first_derivatives_on_gpu_library(oracle):
+    """Engine(Operator::coulomb, max_nprim, max_l, deriv_order = 1).compute2<coulomb, xx_xx, 1> of the reference,
+    UNMODIFIED, on libint2_build_eri1 of the GPU library: twelve shell sets per quartet in canonical and permuted
+    shell orders (the Engine re-maps the derivative index, engine.impl.h:1996-2003), pure and Cartesian shells,
+    against the closed-form derivative integrals at the reference's own thresholds (tests/eri/test.cc:77-88,434-437)."""
+    from util import _sph_matrix, nc
+    rng = np.random.default_rng(515)
+    cases = [((0, 0, 0, 0), None), ((1, 0, 0, 0), None), ((0, 1, 1, 0), None), ((1, 1, 1, 1), None),
+             ((0, 2, 1, 1), (0, 1, 0, 0)), ((2, 1, 0, 2), (1, 0, 0, 1)), ((1, 2, 2, 0), (0, 0, 1, 0)),
+             ((2, 2, 1, 2), (1, 1, 0, 1)), ((2, 2, 2, 2), (1, 0, 1, 0))]
+    for ls, pure in cases:
+        K = 1 if sum(ls) >= 7 else 2
+        l, pu, nprim, O, al, co = random_shell_table(rng, ls, K, pure=pure)
+        sh = oracle.Shells(l, pu, nprim, O, al, co, raw=False)
+        got = oracle.compute2_deriv1(sh, precision=0.0)
+        assert got is not None and got.shape[0] == 12
+        ref = oracle.deriv1_closed(oracle.Shells(l, [0] * 4, nprim, O, al, co, raw=False)).reshape([12] + [nc(x) for x in ls])
+        for ax in range(4):
+            if pu[ax] and ls[ax] > 0:
+                M = _sph_matrix(oracle, ls[ax])
+                ref = np.moveaxis(np.tensordot(M, ref, axes=([1], [ax + 1])), 0, ax + 1)
+        ref = ref.reshape(12, -1)
+        err = np.abs(got - ref)
+        bad = (err > 1e-9 * np.abs(ref)) & (err > 5e-14)
+        assert not bad.any(), (ls, err.max())
+        assert err.max() <= 1e-11 * max(1.0, np.abs(ref).max()), (ls, err.max())
+    # l = 3 is beyond LIBINT2_MAX_AM_eri1 = 2 of the GPU library: lmax_exceeded, as on a libint built that way
+    t = random_shell_table(rng, (3, 0, 0, 0), 1)
+    with pytest.raises(RuntimeError):
+        oracle.compute2_deriv1(oracle.Shells(*t, raw=False), precision=0.0)
+
+
 def test_reference_engine_lmax_exceeded(oracle):
     """four-centre g shells are beyond LIBINT2_MAX_AM_eri of the GPU library: the reference Engine
     reports lmax_exceeded (engine.h:893-916) instead of calling a null table entry."""

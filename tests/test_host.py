@@ -145,7 +145,7 @@ def test_iface_library_exports_the_reference_boundary():
         assert hasattr(L, n), "missing export " + n
     params = open(os.path.join(inc, "libint2_params.h")).read()
     am = {k: int(v) for k, v in re.findall(r"#define LIBINT2_MAX_AM_(\w+) (\d+)", params)}
-    assert am == {"default": 4, "eri": 3, "3eri": 4, "2eri": 4}
+    assert am == {"default": 4, "eri": 3, "3eri": 4, "2eri": 4, "eri1": 2}
     L.libint2_need_memory_eri.restype = ctypes.c_size_t
     L.libint2_need_memory_eri.argtypes = [ctypes.c_int]
     assert L.libint2_need_memory_eri(2) >= 6 ** 4
@@ -158,6 +158,17 @@ def test_iface_library_exports_the_reference_boundary():
     assert tab[idx(1, 0, 1, 0)] and tab[idx(2, 2, 2, 2)] and tab[idx(3, 3, 3, 3)] and tab[idx(1, 1, 3, 0)]
     assert tab[idx(1, 1, 1, 0)] is None            # not canonical: la + lb > lc + ld (build_libint.cc:78-83)
     assert tab[idx(0, 1, 1, 1)] is None            # not canonical: la < lb
+    # first derivatives: libint2_build_eri1, every canonical class of l <= 2 (its raised twins go up to (f d|)
+    assert {"libint2_build_eri1", "libint2_init_eri1", "libint2_need_memory_eri1", "libint2_cleanup_eri1"} <= names
+    assert re.search(r"#define LIBINT2_MAX_DERIV_ORDER 1\b", params)
+    n1 = am["eri1"] + 1
+    tab1 = (ctypes.c_void_p * (n1 ** 4)).in_dll(L, "libint2_build_eri1")
+    idx1 = lambda a, b, c, d: ((a * n1 + b) * n1 + c) * n1 + d
+    assert tab1[idx1(0, 0, 0, 0)] and tab1[idx1(1, 0, 2, 1)] and tab1[idx1(2, 2, 2, 2)]
+    assert tab1[idx1(1, 1, 1, 0)] is None and tab1[idx1(0, 1, 1, 1)] is None
+    L.libint2_need_memory_eri1.restype = ctypes.c_size_t
+    L.libint2_need_memory_eri1.argtypes = [ctypes.c_int]
+    assert L.libint2_need_memory_eri1(2) >= 12 * 6 ** 4
 
 
 def test_generated_iface_headers_are_current(tmp_path):
