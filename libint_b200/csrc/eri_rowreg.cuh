@@ -213,6 +213,54 @@ __device__ __forceinline__ void rr_build_level(Lvl<K::FMAX, F>& out, const P1& p
   });
 }
 
+// The same level with the group barrier INSIDE it: first everything that lives in this lane's registers (the
+// two-term and four-term parts of every value, ~3/4 of the level's FP64 work), then the barrier that makes the
+// cross terms of level F-1 visible, then the cross-term FMAs, the hand-over of this level's values and the targets.
+// A warp that finished level F-1 early computes instead of waiting at the barrier.  (K::EMAX > 0 only.)
+template <class K, int F, bool ACCUM, class P1, class P2, class SyncFn>
+__device__ __forceinline__ void rr_build_level_split(Lvl<K::FMAX, F>& out, const P1& p1, const P2& p2,
+                                                     const double (&QC)[3], const double (&WQ)[3],
+                                                     const double (&koo2e)[6], double roe, const double (&ce)[3],
+                                                     double* __restrict__ Xq, const RowMeta& rmeta,
+                                                     double* __restrict__ acc, SyncFn&& sync) {
+  constexpr int NM = K::FMAX - F + 1;
+  static_for<nc(F)>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    constexpr C3 q = cxyz(F, j);
+    constexpr int d = cdir(q);
+    constexpr int qd = cget(q, d);
+    constexpr int jm1 = cidx(cadd(q, d, -1));
+    static_for<NM>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      double v = QC[d] * p1.v[jm1 * (NM + 1) + m] + WQ[d] * p1.v[jm1 * (NM + 1) + m + 1];
+      if constexpr (qd > 1) {
+        constexpr int jm2 = cidx(cadd(q, d, -2));
+        v += koo2e[qd - 1] * (p2.v[jm2 * (NM + 2) + m] - roe * p2.v[jm2 * (NM + 2) + m + 1]);
+      }
+      out.v[j * NM + m] = v;
+    });
+  });
+  sync();
+  static_for<nc(F)>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    constexpr C3 q = cxyz(F, j);
+    constexpr int d = cdir(q);
+    constexpr int jm1 = cidx(cadd(q, d, -1));
+    static_for<NM>([&](auto mc) {
+      constexpr int m = decltype(mc)::value;
+      const double v = out.v[j * NM + m] + ce[d] * Xq[K::xslot(F - 1, jm1, m + 1) * K::NECX + rmeta.rm[d]];
+      out.v[j * NM + m] = v;
+      if constexpr (F < K::FMAX && m >= 1) {
+        if (rmeta.row < K::NECX) Xq[K::xslot(F, j, m) * K::NECX + rmeta.row] = v;
+      }
+      if constexpr (m == 0 && F >= K::LCv) {
+        if constexpr (ACCUM) acc[nc_upto(F - 1) - K::F0 + j] += v;
+        else acc[nc_upto(F - 1) - K::F0 + j] = v;
+      }
+    });
+  });
+}
+
 template <int LA, int LB, int LC, int LD>
 struct RRK : RR<LA, LB, LC, LD> {
   static constexpr int LCv = LC;

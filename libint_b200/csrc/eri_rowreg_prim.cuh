@@ -377,30 +377,38 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
 
     // ---- [row 0|f 0]^(m), f = 1..FMAX (vrr_11_twoprep_11.h:305-383) -----------------------
     double* Xq = Q + K::OFF_X;
-    if constexpr (FMAX >= 1 && !LB200_DIAG_NOVRR) {
-      sync();
-      Lvl<FMAX, 1> l1;
-      rr_build_level<K, 1, false>(l1, l0, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
-      if constexpr (FMAX >= 2) {
+#ifndef LB200_X_SPLIT
+#define LB200_X_SPLIT 0
+#endif
+    // one level: barrier, then the level (default) -- or the barrier inside the level, after its register-only
+    // part (LB200_X_SPLIT = 1, rr_build_level_split)
+    auto level = [&](auto fc, auto& out, const auto& p1, const auto& p2) {
+      constexpr int F = decltype(fc)::value;
+      if constexpr (LB200_X_SPLIT) {
+        rr_build_level_split<K, F, false>(out, p1, p2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc, sync);
+      } else {
         sync();
+        rr_build_level<K, F, false>(out, p1, p2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+      }
+    };
+    if constexpr (FMAX >= 1 && !LB200_DIAG_NOVRR) {
+      Lvl<FMAX, 1> l1;
+      level(std::integral_constant<int, 1>{}, l1, l0, l0);
+      if constexpr (FMAX >= 2) {
         Lvl<FMAX, 2> l2;
-        rr_build_level<K, 2, false>(l2, l1, l0, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+        level(std::integral_constant<int, 2>{}, l2, l1, l0);
         if constexpr (FMAX >= 3) {
-          sync();
           Lvl<FMAX, 3> l3;
-          rr_build_level<K, 3, false>(l3, l2, l1, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+          level(std::integral_constant<int, 3>{}, l3, l2, l1);
           if constexpr (FMAX >= 4) {
-            sync();
             Lvl<FMAX, 4> l4;
-            rr_build_level<K, 4, false>(l4, l3, l2, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+            level(std::integral_constant<int, 4>{}, l4, l3, l2);
             if constexpr (FMAX >= 5) {
-              sync();
               Lvl<FMAX, 5> l5;
-              rr_build_level<K, 5, false>(l5, l4, l3, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+              level(std::integral_constant<int, 5>{}, l5, l4, l3);
               if constexpr (FMAX >= 6) {
-                sync();
                 Lvl<FMAX, 6> l6;
-                rr_build_level<K, 6, false>(l6, l5, l4, QC, WQ, koo2e, roe, ce, Xq, rmeta, acc);
+                level(std::integral_constant<int, 6>{}, l6, l5, l4);
               }
             }
           }
