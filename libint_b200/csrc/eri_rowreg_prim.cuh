@@ -41,7 +41,12 @@ struct RRP : RRK<LA, LB, LC, LD> {
 #ifndef LB200_PRIM_WIDE35
 #define LB200_PRIM_WIDE35 0
 #endif
-  static constexpr int THREADS = (B::NEC == 35 && LB200_PRIM_WIDE35) ? 256 : B::THREADS;
+  // LB200_PRIM_T35: CTA width of the 35-row kernels (experiments: 160 = 4 quartets, 87.5 % of the lanes)
+#ifndef LB200_PRIM_T35
+#define LB200_PRIM_T35 0
+#endif
+  static constexpr int THREADS = (B::NEC == 35 && LB200_PRIM_T35) ? LB200_PRIM_T35
+                               : ((B::NEC == 35 && LB200_PRIM_WIDE35) ? 256 : B::THREADS);
   static constexpr int GROUP = B::WL ? 32 : THREADS;
   static constexpr int QPG = GROUP / B::NEC;
   static constexpr int NG = THREADS / GROUP;
@@ -73,7 +78,7 @@ struct RRP : RRK<LA, LB, LC, LD> {
 #endif
   static constexpr int MINB128 =
       B::FMAX >= 4 ? LB200_PRIM_MINB_HI : (B::FMAX >= 2 ? LB200_PRIM_MINB_MID : LB200_PRIM_MINB_LO);
-  static constexpr int MINB = THREADS == 256 ? cmax(1, MINB128 / 2) : MINB128;
+  static constexpr int MINB = THREADS == 256 ? cmax(1, MINB128 / 2) : (THREADS > 128 ? cmax(1, MINB128 * 128 / THREADS) : MINB128);
 };
 
 #ifndef LB200_X_NOZERO
