@@ -96,6 +96,49 @@ def test_engine_mirror_deriv1_pure_and_permuted(ctx, oracle):
             assert_reference_thresholds(res[d], ref[d].ravel(), "Engine deriv %s set %d" % (ls, d))
 
 
+def test_deriv1_batch_device_buffers_pure_output_and_edge_cases(ctx, oracle):
+    """device-resident task list and output (torch), solid-harmonic output, an empty batch, a batch whose
+    primitives are all screened out (zeros: the reference returns a null target, engine.impl.h:1781-1784), and a
+    batch larger than one chunk of the derivative scratch"""
+    import torch
+    from libint_b200 import capi
+    po = oracle
+    rng = np.random.default_rng(808)
+    nb = nk = 8
+    bra_sh = _normalized(po, rng, [2] * nb + [1] * nb, 2, pure=[1] * nb + [0] * nb)
+    ket_sh = _normalized(po, rng, [2] * nk + [0] * nk, 1, pure=[1] * nk + [0] * nk)
+    Bb = capi.Basis(ctx, bra_sh.l, bra_sh.pure, bra_sh.nprim, bra_sh.O, bra_sh.alpha, bra_sh.coeff)
+    Bk = capi.Basis(ctx, ket_sh.l, ket_sh.pure, ket_sh.nprim, ket_sh.O, ket_sh.alpha, ket_sh.coeff)
+    bra = capi.Pairs(ctx, Bb, Bb, np.arange(nb), nb + np.arange(nb))
+    ket = capi.Pairs(ctx, Bk, Bk, np.arange(nk), nk + np.arange(nk))
+    tasks = np.array([(i, j) for i in range(nb) for j in range(nk)], dtype=np.int32)
+    cart = capi.eri_deriv1_batch(ctx, bra, ket, tasks)                       # host buffers, Cartesian
+    pure_h = capi.eri_deriv1_batch(ctx, bra, ket, tasks, pure_out=True)      # host buffers, solid harmonics
+    assert cart.shape == (64, 12, 6 * 3 * 6 * 1) and pure_h.shape == (64, 12, 5 * 3 * 5 * 1)
+    M = _sph_matrix(po, 2)
+    ref = np.einsum("pa,tdabcx,qc->tdpbqx", M, cart.reshape(64, 12, 6, 3, 6, 1), M).reshape(64, 12, -1)
+    np.testing.assert_allclose(pure_h, ref, rtol=1e-13, atol=1e-15)
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    t_dev = torch.from_numpy(tasks).to(dev)
+    for pure_out, want in ((False, cart), (True, pure_h)):
+        out = torch.empty(want.shape, dtype=torch.float64, device=dev)
+        capi.eri_deriv1_batch(ctx, bra, ket, t_dev, out=out, pure_out=pure_out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want)
+    # empty batch
+    assert capi.eri_deriv1_batch(ctx, bra, ket, np.zeros((0, 2), dtype=np.int32)).shape == (0, 12, 108)
+    # everything screened out by the engine precision: zeros
+    z = capi.eri_deriv1_batch(ctx, bra, ket, tasks, precision=1e30)
+    assert not z.any()
+    # many tasks: several chunks of the derivative scratch, identical blocks for repeated tasks
+    big = np.tile(tasks, (4000, 1))
+    out = torch.empty((len(big), 12, 108), dtype=torch.float64, device=dev)
+    capi.eri_deriv1_batch(ctx, bra, ket, torch.from_numpy(big).to(dev), out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:64], out[-64:]) and np.array_equal(out[64 * 1234:64 * 1235].cpu().numpy(), cart)
+
+
 def test_deriv1_lmax_is_an_error(ctx, oracle):
     """(f p| would need a (g p| twin: LB200_ERR_LMAX, the analogue of LIBINT2_MAX_AM_eri1"""
     from libint_b200 import capi
