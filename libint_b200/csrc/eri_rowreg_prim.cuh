@@ -437,6 +437,16 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     }
     sync();   // last cross-term reads done: the phase-2 areas alias the cross-term area
     constexpr int TBOFF = K::OFF_B2;
+#ifndef LB200_X_FINPACK
+#define LB200_X_FINPACK 1
+#endif
+    // row stride of the final integrals of an (a 0|c d) class: padded (odd, conflict-free writes by the row lanes)
+    // or, in store mode for the (d s| rows, dense -- the copy-out is then a linear copy of the quartet's block
+    // without the two index divisions per element.  Measured per 2^20 quartets (profiles/r03_variants.txt):
+    // (ds|dd) 0.881 -> 0.801 ms, (ds|dp) 0.529 -> 0.515, (ds|ds) 0.393 -> 0.380; with (p s| rows (three row lanes
+    // per quartet, eight quartets per warp) the dense rows collide in the banks: (ps|dd) 0.391 -> 0.418 -- padded.
+    constexpr bool FINPACK = LB200_X_FINPACK && LB == 0 && !TR && !FOCK && K::NAB >= 6;
+    constexpr int FCS = FINPACK ? K::NCD : K::CS;
     if constexpr (LB > 0) {
       if (valid && rmeta.row >= K::ROW0)
         static_for<K::NCD>([&](auto ic) {
@@ -445,7 +455,7 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     } else {
       if (valid && rmeta.row >= K::ROW0)
         static_for<K::NCD>([&](auto ic) {
-          Q[K::OFF_FIN + (rmeta.row - K::ROW0) * K::CS + decltype(ic)::value] = H[decltype(ic)::value];
+          Q[K::OFF_FIN + (rmeta.row - K::ROW0) * FCS + decltype(ic)::value] = H[decltype(ic)::value];
         });
     }
     cp_async_wait_all();   // own copies of the next round's records have landed ...
@@ -503,10 +513,18 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       double* __restrict__ o = p.out + (size_t)base * BLK;
       if constexpr (!TR) {
         if constexpr (LB == 0) {
-          for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
-            const int q2 = idx / BLK, i = idx - q2 * BLK;
-            const int ab = i / K::NCD, cd = i - ab * K::NCD;
-            o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN + ab * K::CS + cd];
+          if constexpr (FINPACK) {
+            for (int q2 = 0; q2 < nvalid; ++q2) {
+              const double* __restrict__ src = smem + (size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN;
+              double* __restrict__ dst = o + (size_t)q2 * BLK;
+              for (int i = gl; i < BLK; i += GROUP) dst[i] = src[i];
+            }
+          } else {
+            for (int idx = gl; idx < nvalid * BLK; idx += GROUP) {
+              const int q2 = idx / BLK, i = idx - q2 * BLK;
+              const int ab = i / K::NCD, cd = i - ab * K::NCD;
+              o[idx] = smem[(size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN + ab * K::CS + cd];
+            }
           }
         }
       } else {

@@ -16,7 +16,8 @@ CSRC = os.path.join(ROOT, "libint_b200", "csrc")
 LIBDIR = os.path.join(ROOT, "libint_b200", "_lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
-         "-fvisibility=default", "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a"]
+         "-fvisibility=default", "-Xcompiler", "-fno-gnu-unique",   # per-library launcher statics: several variants share a process
+         "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def main():
