@@ -284,6 +284,17 @@ class FockBuilder {
     detail::check(ctx_, rc, "lb200_fock_grad");
     return F2;
   }
+  /// S, T, V of the basis with point charges {Z, x, y, z} per atom: the three compute_1body_ints calls of
+  /// hartree-fock++.cc:267-275 (lb200_onebody on the GPU); row-major nbf x nbf each
+  std::array<std::vector<double>, 3> compute_1body_ints(const std::vector<std::array<double, 4>>& charges) const {
+    std::array<std::vector<double>, 3> M;
+    for (auto& m : M) m.assign((size_t)nbf_ * nbf_, 0.0);
+    std::vector<double> ch;
+    for (const auto& c : charges) ch.insert(ch.end(), c.begin(), c.end());
+    detail::check(ctx_, lb200_onebody(ctx_, bs_, (int)charges.size(), ch.data(), M[0].data(), M[1].data(),
+                                      M[2].data(), 0), "lb200_onebody");
+    return M;
+  }
   /// the Schwarz matrix of compute_schwarz_ints (nshell x nshell)
   std::vector<double> schwarz() const {
     const int ns = lb200_basis_nshell(bs_);

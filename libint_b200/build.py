@@ -71,6 +71,7 @@ def build(jobs=None, force=False, verbose=False):
     if jobs_list or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-Wno-deprecated-gpu-targets", "-ldl"])
     build_iface(force=bool(jobs_list) or force)
+    build_driver(force=bool(jobs_list) or force)
     return LIB
 
 
@@ -91,6 +92,21 @@ def build_iface(force=False):
               # archive, and a second copy inside the .so clashes with the host process's)
               "-L/usr/lib/gcc/x86_64-linux-gnu/13", "-Wl,--exclude-libs,ALL"])
     return IFACE_LIB
+
+
+DRIVER = os.path.join(OUT, "hartree-fock-b200%s" % SUFFIX)
+
+
+def build_driver(force=False):
+    """hartree-fock-b200: the reference's direct-SCF test driver as a C++ host program on the C ABI
+    (csrc/tools/hartree_fock_b200.cc above include/libint_b200.hpp; plain g++, no CUDA headers)."""
+    src = os.path.join(CSRC, "tools", "hartree_fock_b200.cc")
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(inc, "libint_b200.h"), os.path.join(inc, "libint_b200.hpp")]
+    if force or _newer(src, DRIVER, deps):
+        _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-I", inc, src, "-o", DRIVER, "-L", OUT,
+              "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])
+    return DRIVER
 
 
 if __name__ == "__main__":

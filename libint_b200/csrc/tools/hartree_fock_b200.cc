@@ -1,0 +1,417 @@
+// hartree-fock-b200: the reference's direct-SCF test driver (tests/hartree-fock/hartree-fock++.cc, main() :233-716)
+// as a C++ host program on the B200 library -- plain C++17 above include/libint_b200.hpp (the header-only mirror
+// of libint2::Shell / Engine / the Fock builder on the C ABI), no torch, no Python:
+//
+//   hartree-fock-b200 geometry.xyz basis.json [more-basis.json ...] [--codata2010]
+//
+// geometry: XYZ file in Angstrom (libint2::read_dotxyz, atom.h:83-160); basis: packed files under
+// libint_b200/data/basis (the reference's lib/basis/*.g94 re-packed by tools/pack_basis.py); several files are
+// the components of one basis in the reference's sense (aug-cc-pVDZ = cc-pvdz.json augmentation-cc-pvdz.json,
+// basis.h.in:388-400).
+// Steps and conventions follow the reference: nuclear repulsion (:245-255), S/T/V (:267-275; here lb200_onebody
+// on the GPU), conditioned orthogonalizer (:281-290,:1957-2006), core-Hamiltonian start, D = C_occ C_occ^T,
+// E = sum D o (H + F) + E_nuc (:472), error ||FDS - SDF|| / n^2 (:476-477), libint2::DIIS (start 2, depth 5),
+// the Fock precision schedule (:463-466), convergence 1e-12 (:412); the two-electron part of every Fock matrix is
+// lb200_fock_build, the two-body forces (:642-656) are lb200_fock_grad.  Prints the lines the reference's
+// validation scripts parse (hartree-fock++-validate.py:60-70,128-132).  Dense linear algebra of the (small) test
+// systems is a cyclic Jacobi eigensolver on the host.  Exit code 3 = no usable GPU (there is no CPU fallback).
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+#include "libint_b200.hpp"
+
+namespace {
+
+using Matrix = std::vector<double>;   // row-major n x n (or n x m where noted)
+struct Atom { int Z; double x, y, z; };
+
+// ---- minimal JSON reader for the packed basis files: {"name": ..., "shells": {"Z": [[l, [exps], [coefs]], ...]}}
+struct Json {
+  const std::string& s;
+  size_t i = 0;
+  explicit Json(const std::string& text) : s(text) {}
+  void ws() { while (i < s.size() && std::isspace((unsigned char)s[i])) ++i; }
+  bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { ++i; return true; } return false; }
+  void expect(char c) { if (!eat(c)) throw std::runtime_error(std::string("basis file: expected '") + c + "'"); }
+  std::string str() {
+    expect('"');
+    std::string r;
+    while (i < s.size() && s[i] != '"') r += s[i++];
+    ++i;
+    return r;
+  }
+  double num() {
+    ws();
+    char* end = nullptr;
+    const double v = std::strtod(s.c_str() + i, &end);
+    if (end == s.c_str() + i) throw std::runtime_error("basis file: number expected");
+    i = end - s.c_str();
+    return v;
+  }
+  std::vector<double> numlist() {
+    std::vector<double> v;
+    expect('[');
+    if (eat(']')) return v;
+    do v.push_back(num()); while (eat(','));
+    expect(']');
+    return v;
+  }
+};
+struct RawShell { int l; std::vector<double> exps, coefs; };
+
+std::map<int, std::vector<RawShell>> read_basis(const std::string& path, std::string& name) {
+  std::ifstream is(path);
+  if (!is) throw std::runtime_error("cannot open basis file " + path);
+  std::stringstream ss;
+  ss << is.rdbuf();
+  const std::string text = ss.str();
+  Json j(text);
+  std::map<int, std::vector<RawShell>> out;
+  j.expect('{');
+  do {
+    const std::string key = j.str();
+    j.expect(':');
+    if (key == "name") {
+      name = j.str();
+    } else if (key == "shells") {
+      j.expect('{');
+      do {
+        const int Z = std::atoi(j.str().c_str());
+        j.expect(':');
+        j.expect('[');
+        do {
+          RawShell sh;
+          j.expect('[');
+          sh.l = (int)j.num();
+          j.expect(',');
+          sh.exps = j.numlist();
+          j.expect(',');
+          sh.coefs = j.numlist();
+          j.expect(']');
+          out[Z].push_back(sh);
+        } while (j.eat(','));
+        j.expect(']');
+      } while (j.eat(','));
+      j.expect('}');
+    } else {
+      throw std::runtime_error("basis file: unknown key " + key);
+    }
+  } while (j.eat(','));
+  return out;
+}
+
+// basis.h.in:368-386: the 3-21G / 4-31G / 6-31G families use Cartesian d shells
+bool gaussian_cartesian_d_convention(std::string n) {
+  for (auto& c : n) c = (char)std::tolower((unsigned char)c);
+  if (n.rfind("3-21", 0) == 0 || n.rfind("4-31g", 0) == 0) return true;
+  if (n.rfind("6-31", 0) == 0 && n.size() > 4 && n[4] != '1') {
+    const size_t g = n.find('g');
+    if (g == std::string::npos) return false;
+    if (g + 1 == n.size()) return true;
+    if (n[g + 1] == '*' || n[g + 1] == 's') return true;
+  }
+  return false;
+}
+
+std::vector<Atom> read_dotxyz(const std::string& path, double bohr_to_angstrom) {
+  static const char* sym[] = {"x", "h", "he", "li", "be", "b", "c", "n", "o", "f", "ne"};
+  std::ifstream is(path);
+  if (!is) throw std::runtime_error("cannot open geometry file " + path);
+  std::string line;
+  std::getline(is, line);
+  const int natom = std::atoi(line.c_str());
+  std::getline(is, line);   // comment
+  std::vector<Atom> atoms;
+  for (int a = 0; a < natom; ++a) {
+    std::string el;
+    Atom at{};
+    is >> el >> at.x >> at.y >> at.z;
+    for (auto& c : el) c = (char)std::tolower((unsigned char)c);
+    at.Z = -1;
+    for (int z = 1; z <= 10; ++z)
+      if (el == sym[z]) at.Z = z;
+    if (!is || at.Z < 0) throw std::runtime_error("read_dotxyz: bad atom line / element \"" + el + "\"");
+    at.x /= bohr_to_angstrom; at.y /= bohr_to_angstrom; at.z /= bohr_to_angstrom;
+    atoms.push_back(at);
+  }
+  return atoms;
+}
+
+// ---- small dense linear algebra -------------------------------------------------------------------------------
+Matrix matmul(const Matrix& A, const Matrix& B, int n, int k, int m, bool tA = false, bool tB = false) {
+  Matrix C((size_t)n * m, 0.0);   // C[n x m] = op(A)[n x k] op(B)[k x m]
+  for (int i = 0; i < n; ++i)
+    for (int p = 0; p < k; ++p) {
+      const double a = tA ? A[(size_t)p * n + i] : A[(size_t)i * k + p];
+      if (a == 0.0) continue;
+      for (int j = 0; j < m; ++j) C[(size_t)i * m + j] += a * (tB ? B[(size_t)j * k + p] : B[(size_t)p * m + j]);
+    }
+  return C;
+}
+
+// cyclic Jacobi: A (n x n, symmetric) = V diag(w) V^T, eigenvalues ascending
+void jacobi_eigh(Matrix A, int n, std::vector<double>& w, Matrix& V) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[(size_t)p * n + q];
+        if (std::abs(apq) < 1e-300) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {   // columns p, q
+          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * akp - s * akq;
+          A[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {   // rows p, q
+          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)p * n + k] = c * apk - s * aqk;
+          A[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+          V[(size_t)k * n + p] = c * vkp - s * vkq;
+          V[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  std::vector<int> ord(n);
+  for (int i = 0; i < n; ++i) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](int a, int b) { return A[(size_t)a * n + a] < A[(size_t)b * n + b]; });
+  w.resize(n);
+  Matrix Vs((size_t)n * n);
+  for (int j = 0; j < n; ++j) {
+    w[j] = A[(size_t)ord[j] * n + ord[j]];
+    for (int i = 0; i < n; ++i) Vs[(size_t)i * n + j] = V[(size_t)i * n + ord[j]];
+  }
+  V.swap(Vs);
+}
+
+// solve B c = rhs (small, dense) by Gaussian elimination with partial pivoting; false if singular
+bool solve(std::vector<double> B, std::vector<double> rhs, int n, std::vector<double>& c) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i)
+      if (std::abs(B[(size_t)i * n + k]) > std::abs(B[(size_t)piv * n + k])) piv = i;
+    if (std::abs(B[(size_t)piv * n + k]) < 1e-300) return false;
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) std::swap(B[(size_t)k * n + j], B[(size_t)piv * n + j]);
+      std::swap(rhs[k], rhs[piv]);
+    }
+    for (int i = k + 1; i < n; ++i) {
+      const double f = B[(size_t)i * n + k] / B[(size_t)k * n + k];
+      for (int j = k; j < n; ++j) B[(size_t)i * n + j] -= f * B[(size_t)k * n + j];
+      rhs[i] -= f * rhs[k];
+    }
+  }
+  c.assign(n, 0.0);
+  for (int i = n - 1; i >= 0; --i) {
+    double s = rhs[i];
+    for (int j = i + 1; j < n; ++j) s -= B[(size_t)i * n + j] * c[j];
+    c[i] = s / B[(size_t)i * n + i];
+  }
+  return true;
+}
+
+// libint2::DIIS (include/libint2/diis.h), start 2, depth 5
+struct DIIS {
+  std::vector<Matrix> x, e;
+  int iter = 0;
+  Matrix extrapolate(const Matrix& F, const Matrix& err) {
+    ++iter;
+    x.push_back(F);
+    e.push_back(err);
+    if (x.size() > 5) { x.erase(x.begin()); e.erase(e.begin()); }
+    const int n = (int)x.size();
+    if (iter < 2 || n < 2) return F;
+    std::vector<double> B((size_t)(n + 1) * (n + 1), 0.0), rhs(n + 1, 0.0), c;
+    double scale = 1e-300;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (size_t k = 0; k < err.size(); ++k) s += e[i][k] * e[j][k];
+        B[(size_t)i * (n + 1) + j] = s;
+        scale = std::max(scale, std::abs(s));
+      }
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j < n; ++j) B[(size_t)i * (n + 1) + j] /= scale;
+      B[(size_t)i * (n + 1) + n] = B[(size_t)n * (n + 1) + i] = -1.0;
+    }
+    rhs[n] = -1.0;
+    if (!solve(B, rhs, n + 1, c)) return F;
+    Matrix out(F.size(), 0.0);
+    for (int i = 0; i < n; ++i)
+      for (size_t k = 0; k < F.size(); ++k) out[k] += c[i] * x[i][k];
+    return out;
+  }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s geometry.xyz basis.json [more-basis.json ...] [--codata2010]\n", argv[0]);
+    return 2;
+  }
+  try {
+    bool codata2010 = false;
+    std::vector<std::string> basis_files;
+    for (int a = 2; a < argc; ++a) {
+      if (!std::strcmp(argv[a], "--codata2010")) codata2010 = true;
+      else basis_files.push_back(argv[a]);
+    }
+    if (basis_files.empty()) throw std::runtime_error("no basis file given");
+    const double b2a = codata2010 ? 0.52917721092 /* atom.h:63, hartree-fock.cc:306 */ : 0.529177210903 /* atom.h:53 */;
+    const std::vector<Atom> atoms = read_dotxyz(argv[1], b2a);
+    std::string bname;
+    std::vector<std::map<int, std::vector<RawShell>>> comps;
+    for (const std::string& f : basis_files) {
+      std::string nm;
+      comps.push_back(read_basis(f, nm));
+      if (bname.empty()) bname = nm;
+    }
+    const bool cart_d = gaussian_cartesian_d_convention(bname);
+    // BasisSet(name, atoms): the element's shells moved to every atom (basis.h.in:99-148)
+    std::vector<libint_b200::Shell> obs;
+    std::vector<int> shell2atom;
+    for (size_t a = 0; a < atoms.size(); ++a) {
+      for (const auto& lib : comps) {
+        const auto it = lib.find(atoms[a].Z);
+        if (it == lib.end()) throw std::runtime_error("basis " + bname + " lacks element Z=" + std::to_string(atoms[a].Z));
+        for (const RawShell& r : it->second) {
+          obs.emplace_back(r.exps, r.l, cart_d ? r.l > 2 : r.l > 1, r.coefs,
+                           std::array<double, 3>{{atoms[a].x, atoms[a].y, atoms[a].z}});
+          shell2atom.push_back((int)a);
+        }
+      }
+    }
+    std::printf("Atomic Cartesian coordinates (a.u.):\n");
+    int nelec = 0;
+    for (const Atom& a : atoms) {
+      std::printf("%d %.10f %.10f %.10f\n", a.Z, a.x, a.y, a.z);
+      nelec += a.Z;
+    }
+    if (nelec % 2) throw std::runtime_error("RHF needs an even number of electrons");
+    const int ndocc = nelec / 2;
+    double enuc = 0.0;   // :245-255
+    for (size_t i = 0; i < atoms.size(); ++i)
+      for (size_t j = 0; j < i; ++j)
+        enuc += atoms[i].Z * atoms[j].Z / std::sqrt(std::pow(atoms[i].x - atoms[j].x, 2) + std::pow(atoms[i].y - atoms[j].y, 2) +
+                                                    std::pow(atoms[i].z - atoms[j].z, 2));
+
+    libint_b200::FockBuilder fb(obs);
+    const int n = fb.nbf();
+    std::printf("orbital basis set rank = %d\n", n);
+    std::printf("Nuclear repulsion energy = %.12f\n", enuc);
+    std::vector<std::array<double, 4>> charges;
+    for (const Atom& a : atoms) charges.push_back({{(double)a.Z, a.x, a.y, a.z}});
+    const auto STV = fb.compute_1body_ints(charges);
+    const Matrix& S = STV[0];
+    Matrix H((size_t)n * n);
+    for (size_t k = 0; k < H.size(); ++k) H[k] = STV[1][k] + STV[2][k];
+
+    // conditioning orthogonalizer (:281-290,:1957-2006): X = U w^-1/2 on the eigenvalues >= w_max / 1e8
+    std::vector<double> w;
+    Matrix U;
+    jacobi_eigh(S, n, w, U);
+    int first = 0;
+    while (first < n && w[first] < w[n - 1] / 1e8) ++first;
+    const int r = n - first;
+    const double cond = w[n - 1] / w[first];
+    Matrix X((size_t)n * r);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < r; ++j) X[(size_t)i * r + j] = U[(size_t)i * n + first + j] / std::sqrt(w[first + j]);
+
+    Matrix C;
+    std::vector<double> evals;
+    auto density = [&](const Matrix& F) {
+      const Matrix XtF = matmul(X, F, r, n, n, true);
+      const Matrix Fp = matmul(XtF, X, r, n, r);
+      Matrix Cp;
+      jacobi_eigh(Fp, r, evals, Cp);
+      C = matmul(X, Cp, n, r, r);
+      Matrix D((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double s = 0.0;
+          for (int o = 0; o < ndocc; ++o) s += C[(size_t)i * r + o] * C[(size_t)j * r + o];
+          D[(size_t)i * n + j] = s;
+        }
+      return D;
+    };
+
+    Matrix D = density(H), F = H;
+    DIIS diis;
+    double ehf = 0.0, rms = 1.0, ediff_rel = 0.0;
+    const double eps = std::numeric_limits<double>::epsilon();
+    int it = 0;
+    std::printf("\n\nIter         E(HF)                 D(E)/E         RMS([F,D])/nn\n");
+    while (true) {
+      ++it;
+      const double ehf_last = ehf;
+      const double precision = std::min(std::min(1e-3 / cond, 1e-7), std::max(rms / 1e4, eps));   // :463-466
+      const Matrix G = fb.compute_2body_fock(D, precision);
+      for (size_t k = 0; k < F.size(); ++k) F[k] = H[k] + G[k];
+      ehf = 0.0;
+      for (size_t k = 0; k < F.size(); ++k) ehf += D[k] * (H[k] + F[k]);
+      ediff_rel = std::abs((ehf - ehf_last) / ehf);
+      const Matrix FD = matmul(F, D, n, n, n), FDS = matmul(FD, S, n, n, n);
+      Matrix comm((size_t)n * n);
+      double nrm = 0.0;
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          comm[(size_t)i * n + j] = FDS[(size_t)i * n + j] - FDS[(size_t)j * n + i];   // SDF = (FDS)^T
+          nrm += comm[(size_t)i * n + j] * comm[(size_t)i * n + j];
+        }
+      rms = std::sqrt(nrm) / ((double)n * n);
+      D = density(diis.extrapolate(F, comm));
+      std::printf(" %02d %20.12f %20.12e %20.12e\n", it, ehf + enuc, ediff_rel, rms);
+      if (!((ediff_rel > 1e-12 || rms > 1e-12) && it < 100)) break;
+    }
+    const bool converged = ediff_rel <= 1e-12 && rms <= 1e-12;
+    std::printf("%s\n", converged ? "converged" : "NOT converged");
+    std::printf("** Hartree-Fock energy = %20.12f\n", ehf + enuc);
+
+    // forces available from this library: two-body (compute_2body_fock_deriv<1> traced with D, :642-656) and
+    // nuclear repulsion (:668-701); the one-body and Pulay parts need Engine::compute1 derivatives (Python driver)
+    try {
+      const auto F2 = fb.compute_2body_forces(D, shell2atom, (int)atoms.size(), eps, /*use_schwarz=*/false);
+      std::printf("** 2-body forces = ");
+      for (double v : F2) std::printf("%.15g ", v);
+      std::printf("\n");
+    } catch (const libint_b200::lmax_exceeded& e) {
+      std::printf("2-body forces skipped: %s\n", e.what());
+    }
+    std::vector<double> FN(3 * atoms.size(), 0.0);
+    for (size_t a1 = 1; a1 < atoms.size(); ++a1)
+      for (size_t a2 = 0; a2 < a1; ++a2) {
+        const double d[3] = {atoms[a1].x - atoms[a2].x, atoms[a1].y - atoms[a2].y, atoms[a1].z - atoms[a2].z};
+        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const double f = atoms[a1].Z * atoms[a2].Z / (std::sqrt(r2) * r2);
+        for (int k = 0; k < 3; ++k) { FN[3 * a1 + k] -= d[k] * f; FN[3 * a2 + k] += d[k] * f; }
+      }
+    std::printf("** nuclear repulsion forces = ");
+    for (double v : FN) std::printf("%.15g ", v);
+    std::printf("\n");
+    return converged ? 0 : 1;
+  } catch (const libint_b200::error& e) {
+    std::fprintf(stderr, "libint_b200::error: %s (there is no CPU fallback)\n", e.what());
+    return std::strstr(e.what(), "(-2)") ? 3 : 4;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 4;
+  }
+}

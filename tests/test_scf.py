@@ -235,6 +235,59 @@ def test_gpu_forces_match_the_reference_golden_values(ctx):
         assert err < tol, "%s forces: max deviation %.3g (tolerance %g)" % (key, err, tol)
 
 
+def _cxx_driver_inputs(tmp_path):
+    import os
+    from libint_b200 import basis as b
+    from libint_b200 import build
+    exe = build.build_driver()
+    (tmp_path / "h2o.xyz").write_text("3\n\n" + "".join(
+        "%s %.5f %.5f %.5f\n" % ({8: "O", 1: "H"}[Z], *r) for Z, r in b.H2O_XYZ_ANGSTROM))
+    (tmp_path / "h2o_rotated.xyz").write_text("3\nrotated water\n" + "".join(
+        "%s %.17g %.17g %.17g\n" % ({8: "O", 1: "H"}[Z], *r) for Z, r in b.H2O_ROTATED_XYZ_ANGSTROM))
+    data = os.path.join(os.path.dirname(os.path.abspath(b.__file__)), "data", "basis")
+    return exe, data
+
+
+@pytest.mark.gpu
+def test_cxx_driver_reproduces_the_reference_goldens(tmp_path):
+    """hartree-fock-b200 (C++ host program on the C ABI, no Python in the loop): the reference's golden SCF
+    energies and, for its validation run, the golden two-body and nuclear-repulsion forces
+    (hartree-fock-validate.py:14, hartree-fock++-validate.py:49,97-107), parsed with the validators' patterns."""
+    import os
+    import re
+    import subprocess
+    exe, data = _cxx_driver_inputs(tmp_path)
+    num = r"\s*([+-]?(?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?)"
+    cases = [([str(tmp_path / "h2o.xyz"), os.path.join(data, "sto-3g.json"), "--codata2010"], -74.942080057696, 1e-11, False),
+             ([str(tmp_path / "h2o_rotated.xyz"), os.path.join(data, "cc-pvdz.json"),
+               os.path.join(data, "augmentation-cc-pvdz.json")], -76.003354058439, 5e-12, True)]
+    for argv, eref, tol, forces in cases:
+        r = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        m = [re.match(r"\*\* Hartree-Fock energy =" + num, ln) for ln in r.stdout.splitlines()]
+        m = [x for x in m if x]
+        assert len(m) == 1 and abs(float(m[0].group(1)) - eref) < tol, r.stdout[-600:]
+        if forces:
+            for key in ("2-body", "nuclear repulsion"):
+                ref, ftol = REF_FORCES[key]
+                mm = [re.match(r"\*\* %s forces =" % re.escape(key) + num * 9, ln) for ln in r.stdout.splitlines()]
+                mm = [x for x in mm if x]
+                assert len(mm) == 1, key
+                assert max(abs(float(v) - x) for v, x in zip(mm[0].groups(), ref)) < ftol, key
+
+
+def test_cxx_driver_fails_loudly_without_gpu(tmp_path):
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe, data = _cxx_driver_inputs(tmp_path)
+    r = subprocess.run([exe, str(tmp_path / "h2o.xyz"), os.path.join(data, "sto-3g.json")], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    assert "Hartree-Fock energy" not in r.stdout
+
+
 def test_hartree_fock_cli_fails_loudly_without_gpu():
     import os
     import subprocess
