@@ -2,7 +2,7 @@
 // as a C++ host program on the B200 library -- plain C++17 above include/libint_b200.hpp (the header-only mirror
 // of libint2::Shell / Engine / the Fock builder on the C ABI), no torch, no Python:
 //
-//   hartree-fock-b200 geometry.xyz basis.json [more-basis.json ...] [--codata2010]
+//   hartree-fock-b200 geometry.xyz basis.json [more-basis.json ...] [--codata2010] [--dump-basis]
 //
 // geometry: XYZ file in Angstrom (libint2::read_dotxyz, atom.h:83-160); basis: packed files under
 // libint_b200/data/basis (the reference's lib/basis/*.g94 re-packed by tools/pack_basis.py); several files are
@@ -267,10 +267,11 @@ int main(int argc, char** argv) {
     return 2;
   }
   try {
-    bool codata2010 = false;
+    bool codata2010 = false, dump_basis = false;
     std::vector<std::string> basis_files;
     for (int a = 2; a < argc; ++a) {
       if (!std::strcmp(argv[a], "--codata2010")) codata2010 = true;
+      else if (!std::strcmp(argv[a], "--dump-basis")) dump_basis = true;   // host-only: print the shells and stop
       else basis_files.push_back(argv[a]);
     }
     if (basis_files.empty()) throw std::runtime_error("no basis file given");
@@ -297,6 +298,18 @@ int main(int argc, char** argv) {
           shell2atom.push_back((int)a);
         }
       }
+    }
+    if (dump_basis) {   // l pure nprim Ox Oy Oz, then exponents, then normalization-embedded coefficients
+      std::printf("%zu\n", obs.size());
+      for (size_t i = 0; i < obs.size(); ++i) {
+        const auto& sh = obs[i];
+        std::printf("%d %d %zu %.17g %.17g %.17g %d\n", sh.l, sh.pure ? 1 : 0, sh.nprim(), sh.O[0], sh.O[1], sh.O[2], shell2atom[i]);
+        for (double x : sh.alpha) std::printf("%.17g ", x);
+        std::printf("\n");
+        for (double x : sh.coeff) std::printf("%.17g ", x);
+        std::printf("\n");
+      }
+      return 0;
     }
     std::printf("Atomic Cartesian coordinates (a.u.):\n");
     int nelec = 0;

@@ -276,6 +276,31 @@ def test_cxx_driver_reproduces_the_reference_goldens(tmp_path):
                 assert max(abs(float(v) - x) for v, x in zip(mm[0].groups(), ref)) < ftol, key
 
 
+def test_cxx_driver_basis_reader_matches_the_python_mirror(tmp_path):
+    """CPU: the C++ driver's host side -- xyz reader, packed-basis reader, the pure / Cartesian-d rule of
+    BasisSet (basis.h.in:368-386), component order of aug-cc-pVDZ (:388-400), Shell::renorm through the C ABI --
+    builds the same shells as libint_b200.basis.BasisSet (itself checked against the reference's reader)."""
+    import os
+    import subprocess
+    from libint_b200.basis import BasisSet
+    exe, data = _cxx_driver_inputs(tmp_path)
+    for geom, files, name in [("h2o", ["sto-3g.json"], "sto-3g"), ("h2o", ["6-31gs.json"], "6-31g*"),
+                              ("h2o_rotated", ["cc-pvdz.json", "augmentation-cc-pvdz.json"], "aug-cc-pvdz"),
+                              ("h2o", ["def2-tzvp.json"], "def2-tzvp")]:
+        r = subprocess.run([exe, str(tmp_path / (geom + ".xyz"))] + [os.path.join(data, f) for f in files] +
+                           ["--dump-basis"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().splitlines()
+        bs = BasisSet(name, _atoms(geom))
+        assert int(lines[0]) == len(bs)
+        for i, sh in enumerate(bs):
+            h = lines[1 + 3 * i].split()
+            assert [int(h[0]), int(h[1]), int(h[2]), int(h[6])] == [sh.l, int(sh.pure), sh.nprim, bs.shell2atom[i]]
+            np.testing.assert_allclose([float(x) for x in h[3:6]], sh.O, rtol=0, atol=2e-10)   # xyz file: 5 digits
+            np.testing.assert_array_equal([float(x) for x in lines[2 + 3 * i].split()], sh.alpha)
+            np.testing.assert_array_equal([float(x) for x in lines[3 + 3 * i].split()], sh.coeff)
+
+
 def test_cxx_driver_fails_loudly_without_gpu(tmp_path):
     import os
     import subprocess
