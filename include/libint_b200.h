@@ -210,6 +210,18 @@ int lb200_eri_product(lb200_context* ctx, const lb200_pairs* bra, const lb200_pa
 int lb200_onebody(lb200_context* ctx, const lb200_basis* bs, int natom, const double* charges, double* S,
                   double* T, double* V, int on_device);
 
+/* ---- one-body contributions to the nuclear forces, the first block of the reference driver's force section
+ *      (tests/hartree-fock/hartree-fock++.cc:601-627):  F1[3 atom + xyz] = 2 sum_ij (T1 + V1)_ij D_ij  and
+ *      FPulay[3 atom + xyz] = -2 sum_ij S1_ij W_ij  with S1 / T1 / V1 = compute_1body_ints_deriv<overlap | kinetic |
+ *      nuclear>(1, obs, atoms) (:1154-1228; Engine::compute1 with deriv_order 1) and W = C_occ eps_occ C_occ^T.  The
+ *      3 natom derivative matrices are never formed: each shell pair's derivative integrals are contracted with its
+ *      density block on the GPU.  charges = natom x {Z, x, y, z} (host); shell2atom[nshell] (host;
+ *      BasisSet::shell2atom); D, W = nbf x nbf row-major, device (on_device = 1) or host; F1, FPulay: host,
+ *      3 natom doubles each.  LB200_ERR_LMAX if a shell has l > 4. */
+int lb200_onebody_forces(lb200_context* ctx, const lb200_basis* bs, int natom, const double* charges,
+                         const int* shell2atom, const double* D, const double* W, int on_device, double* F1,
+                         double* FPulay);
+
 /* ---- density fitting: three-centre integrals (P|mu nu) as dense slabs and the two-centre metric (P|Q):
  *      the DF set-up of tests/hartree-fock/hartree-fock++.cc:2215-2262 (Zxy[ndf][n][n] via
  *      Engine::compute2<coulomb, xs_xx>(dfbs[s1], Shell::unit(), obs[s2], obs[s3])) and

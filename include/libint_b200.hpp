@@ -295,6 +295,24 @@ class FockBuilder {
                                       M[2].data(), 0), "lb200_onebody");
     return M;
   }
+  /// One-body and Pulay contributions to the forces, {F1, F_Pulay}, 3 * natoms each (hartree-fock++.cc:601-627):
+  /// F1 = 2 sum (T1 + V1) o D, F_Pulay = -2 sum S1 o W with the first-derivative integrals of
+  /// compute_1body_ints_deriv (:1154-1228) contracted on the GPU (lb200_onebody_forces); W = C_occ eps_occ C_occ^T.
+  std::array<std::vector<double>, 2> compute_1body_forces(const std::vector<std::array<double, 4>>& charges,
+                                                          const std::vector<int>& shell2atom,
+                                                          const std::vector<double>& D,
+                                                          const std::vector<double>& W) const {
+    if ((long long)D.size() != (long long)nbf_ * nbf_ || W.size() != D.size())
+      throw std::invalid_argument("FockBuilder: D / W size");
+    if ((int)shell2atom.size() != lb200_basis_nshell(bs_)) throw std::invalid_argument("FockBuilder: shell2atom size");
+    std::array<std::vector<double>, 2> F;
+    for (auto& f : F) f.assign(3 * charges.size(), 0.0);
+    std::vector<double> ch;
+    for (const auto& c : charges) ch.insert(ch.end(), c.begin(), c.end());
+    detail::check(ctx_, lb200_onebody_forces(ctx_, bs_, (int)charges.size(), ch.data(), shell2atom.data(), D.data(),
+                                             W.data(), 0, F[0].data(), F[1].data()), "lb200_onebody_forces");
+    return F;
+  }
   /// the Schwarz matrix of compute_schwarz_ints (nshell x nshell)
   std::vector<double> schwarz() const {
     const int ns = lb200_basis_nshell(bs_);

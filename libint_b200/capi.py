@@ -68,6 +68,7 @@ SIGNATURES = {
     "lb200_fock_destroy": (C.c_int, [vp]),
     "lb200_fock_schwarz": (C.c_int, [vp, dp]),
     "lb200_onebody": (C.c_int, [vp, vp, C.c_int, dp, vp, vp, vp, C.c_int]),
+    "lb200_onebody_forces": (C.c_int, [vp, vp, C.c_int, dp, ip, vp, vp, C.c_int, dp, dp]),
     "lb200_eri_product": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]),
     "lb200_df3c_create": (C.c_int, [vp, vp, vp, C.c_longlong, ip, ip, C.POINTER(vp)]),
     "lb200_df3c_destroy": (C.c_int, [vp]),
@@ -423,6 +424,31 @@ def onebody(ctx, basis, charges, device=False):
     ctx.check(load().lb200_onebody(ctx.h, basis.h, len(ch), _d(ch), vp(M[0].ctypes.data), vp(M[1].ctypes.data),
                                    vp(M[2].ctypes.data), 0), "onebody")
     return M
+
+
+def onebody_forces(ctx, basis, charges, shell2atom, D, W):
+    """(F1, F_Pulay), each [natom, 3]: 2 sum (T1 + V1) o D and -2 sum S1 o W of hartree-fock++.cc:601-627 on the GPU
+    (lb200_onebody_forces).  D, W: numpy arrays or torch CUDA tensors (both of one kind), nbf x nbf."""
+    ch = np.ascontiguousarray([[z, c[0], c[1], c[2]] for z, c in charges], dtype=np.float64).reshape(-1, 4)
+    s2a = np.ascontiguousarray(shell2atom, dtype=np.int32)
+    if len(s2a) != basis.nshell:
+        raise ValueError("onebody_forces: shell2atom needs one entry per shell")
+    n = basis.nbf
+    F1, FP = np.zeros((len(ch), 3)), np.zeros((len(ch), 3))
+    if isinstance(D, np.ndarray) != isinstance(W, np.ndarray):
+        raise ValueError("onebody_forces: D and W must both be numpy arrays or both be torch CUDA tensors")
+    if isinstance(D, np.ndarray):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        pD, pW, on_dev = vp(D.ctypes.data), vp(W.ctypes.data), 0
+    else:
+        D, W = D.contiguous(), W.contiguous()
+        pD, pW, on_dev = vp(D.data_ptr()), vp(W.data_ptr()), 1
+    if tuple(D.shape) != (n, n) or tuple(W.shape) != (n, n):
+        raise ValueError("onebody_forces: D and W must be nbf x nbf")
+    ctx.check(load().lb200_onebody_forces(ctx.h, basis.h, len(ch), _d(ch), _i(s2a), pD, pW, on_dev, _d(F1), _d(FP)),
+              "onebody_forces")
+    return F1, FP
 
 
 def eri_product(ctx, bra, ket, b0, nb, k0, nk, out, screening=SCREEN_ORIGINAL, precision=0.0, pure_out=False):

@@ -12,7 +12,7 @@
 // on the GPU), conditioned orthogonalizer (:281-290,:1957-2006), core-Hamiltonian start, D = C_occ C_occ^T,
 // E = sum D o (H + F) + E_nuc (:472), error ||FDS - SDF|| / n^2 (:476-477), libint2::DIIS (start 2, depth 5),
 // the Fock precision schedule (:463-466), convergence 1e-12 (:412); the two-electron part of every Fock matrix is
-// lb200_fock_build, the two-body forces (:642-656) are lb200_fock_grad.  Prints the lines the reference's
+// lb200_fock_build; the force block (:596-716) is lb200_onebody_forces + lb200_fock_grad.  Prints the lines the reference's
 // validation scripts parse (hartree-fock++-validate.py:60-70,128-132).  Dense linear algebra of the (small) test
 // systems is a cyclic Jacobi eigensolver on the host.  Exit code 3 = no usable GPU (there is no CPU fallback).
 #include <cctype>
@@ -398,17 +398,33 @@ int main(int argc, char** argv) {
     std::printf("%s\n", converged ? "converged" : "NOT converged");
     std::printf("** Hartree-Fock energy = %20.12f\n", ehf + enuc);
 
-    // forces available from this library: two-body (compute_2body_fock_deriv<1> traced with D, :642-656) and
-    // nuclear repulsion (:668-701); the one-body and Pulay parts need Engine::compute1 derivatives (Python driver)
-    try {
-      const auto F2 = fb.compute_2body_forces(D, shell2atom, (int)atoms.size(), eps, /*use_schwarz=*/false);
-      std::printf("** 2-body forces = ");
-      for (double v : F2) std::printf("%.15g ", v);
+    // the force block of the reference driver (:596-716), in its output format (parsed by
+    // hartree-fock++-validate.py:128-132): one-body and Pulay parts from lb200_onebody_forces (:601-627), the two-body
+    // part from lb200_fock_grad (compute_2body_fock_deriv<1> traced with D, :642-656), nuclear repulsion (:668-701)
+    const size_t n3 = 3 * atoms.size();
+    auto print_forces = [&](const char* key, const std::vector<double>& f) {
+      std::printf("** %s forces = ", key);
+      for (double v : f) std::printf("%.15g ", v);
       std::printf("\n");
+    };
+    Matrix W((size_t)n * n, 0.0);   // orbital-energy-weighted density C_occ eps_occ C_occ^T (:617-619)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int o = 0; o < ndocc; ++o) s += C[(size_t)i * r + o] * evals[o] * C[(size_t)j * r + o];
+        W[(size_t)i * n + j] = s;
+      }
+    const auto F1P = fb.compute_1body_forces(charges, shell2atom, D, W);
+    print_forces("1-body", F1P[0]);
+    print_forces("Pulay", F1P[1]);
+    std::vector<double> F2;
+    try {
+      F2 = fb.compute_2body_forces(D, shell2atom, (int)atoms.size(), eps, /*use_schwarz=*/false);
+      print_forces("2-body", F2);
     } catch (const libint_b200::lmax_exceeded& e) {
       std::printf("2-body forces skipped: %s\n", e.what());
     }
-    std::vector<double> FN(3 * atoms.size(), 0.0);
+    std::vector<double> FN(n3, 0.0);
     for (size_t a1 = 1; a1 < atoms.size(); ++a1)
       for (size_t a2 = 0; a2 < a1; ++a2) {
         const double d[3] = {atoms[a1].x - atoms[a2].x, atoms[a1].y - atoms[a2].y, atoms[a1].z - atoms[a2].z};
@@ -416,9 +432,12 @@ int main(int argc, char** argv) {
         const double f = atoms[a1].Z * atoms[a2].Z / (std::sqrt(r2) * r2);
         for (int k = 0; k < 3; ++k) { FN[3 * a1 + k] -= d[k] * f; FN[3 * a2 + k] += d[k] * f; }
       }
-    std::printf("** nuclear repulsion forces = ");
-    for (double v : FN) std::printf("%.15g ", v);
-    std::printf("\n");
+    print_forces("nuclear repulsion", FN);
+    if (!F2.empty()) {
+      std::vector<double> Ftot(n3);
+      for (size_t k = 0; k < n3; ++k) Ftot[k] = F1P[0][k] + F1P[1][k] + F2[k] + FN[k];
+      print_forces("Hartree-Fock", Ftot);
+    }
     return converged ? 0 : 1;
   } catch (const libint_b200::error& e) {
     std::fprintf(stderr, "libint_b200::error: %s (there is no CPU fallback)\n", e.what());

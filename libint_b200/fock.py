@@ -116,6 +116,20 @@ class FockBuilder:
             g = allreduce_forces(g, self.ctx.device)
         return (g, st) if stats else g
 
+    def forces_1body(self, D, W, atoms):
+        """One-body and Pulay contributions to the forces, (F1, F_Pulay) each [natoms, 3]
+        (hartree-fock++.cc:601-627; lb200_onebody_forces on the GPU).  D: density, W = C_occ eps_occ C_occ^T, numpy
+        or torch CUDA tensors; atoms: the molecule (point charges and force centres).  Every rank evaluates the
+        whole (set-up-sized) sum: no reduction."""
+        shell2atom = self.obs.shell2atom
+        if len(shell2atom) == 0 or min(shell2atom) < 0:
+            raise ValueError("forces_1body needs shell2atom (the basis was built from bare shells)")
+        if not isinstance(D, np.ndarray):
+            import torch
+            self.ctx.set_stream(torch.cuda.current_stream(torch.device("cuda", self.ctx.device)).cuda_stream)
+        charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+        return capi.onebody_forces(self.ctx, self.basis, charges, shell2atom, D, W)
+
     def __call__(self, D, precision=1e-12, use_schwarz=True):
         """Full G on every rank. With torch CUDA input the result is a torch CUDA tensor and the
         reduction is NCCL; with numpy input on one rank the result is numpy."""

@@ -7,8 +7,8 @@ default geometry h2o.xyz, default basis aug-cc-pVDZ) and prints the lines the re
 validation scripts parse (`** Hartree-Fock energy = ...`, hartree-fock++-validate.py:60-70,
 hartree-fock-validate.py:19-24; `** 1-body forces = ...` to `** Hartree-Fock forces = ...`,
 hartree-fock++-validate.py:128-132), so those scripts can be pointed at this driver unchanged.
-The two-electron part of every Fock matrix comes from the CUDA path (lb200_fock_build), the two-body
-forces from lb200_fock_grad; `--codata2010` converts Angstrom with the constant the plain `hartree-fock` test uses
+S, T, V come from lb200_onebody, the two-electron part of every Fock matrix from lb200_fock_build, the one-body
+and Pulay forces from lb200_onebody_forces, the two-body forces from lb200_fock_grad (all on the GPU); `--codata2010` converts Angstrom with the constant the plain `hartree-fock` test uses
 (hartree-fock.cc:306) instead of libint2's CODATA-2018 default.
 """
 import argparse
@@ -42,7 +42,9 @@ def main(argv=None):
         print("%d %.10f %.10f %.10f" % (a.atomic_number, a.x, a.y, a.z))
     print("orbital basis set rank = %d" % obs.nbf)
     fb = FockBuilder(obs, device=args.device, rank=0, nranks=1)
-    scf = RHF(obs, atoms, lambda D, prec: fb.build_partial(np.ascontiguousarray(D), prec))
+    charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+    scf = RHF(obs, atoms, lambda D, prec: fb.build_partial(np.ascontiguousarray(D), prec),
+              stv=capi.onebody(fb.ctx, fb.basis, charges))   # S, T, V from lb200_onebody
     print("Nuclear repulsion energy = %.12f" % scf.enuc)
     print("\n\nIter         E(HF)                 D(E)/E         RMS([F,D])/nn       Time(s)")
     t0 = time.time()

@@ -189,8 +189,10 @@ def nuclear_repulsion(atoms):
 
 
 # ---------------------------------------------------------------------------------------------------
-# first derivatives of S, T, V (host numpy, like the integrals above: NOT the GPU hot path).  They close
-# the force expression of the reference's driver around the GPU two-body gradient:
+# first derivatives of S, T, V in numpy: the CHECKER of the GPU one-body force kernel (lb200_onebody_forces,
+# csrc/onebody_deriv.cu), not a product path -- scf.hf_forces and the C++ driver call the GPU entry.  These
+# derivative matrices are pinned on the CPU against the reference's golden forces (tests/test_scf.py) and then
+# serve as the reference of the kernel's CPU-compiled core and of the kernel itself.
 # compute_1body_ints_deriv<overlap|kinetic|nuclear>(1, obs, atoms), hartree-fock++.cc:1154-1228, used at
 # :601-627.  d/dA_x (a|O|b) = 2 alpha (a+1_x|O|b) - a_x (a-1_x|O|b); the derivative with respect to a
 # nuclear position follows from translational invariance of every single-charge term.

@@ -64,14 +64,16 @@ def conditioning_orthogonalizer(S, max_condition_number=1e8):
 
 
 class RHF:
-    def __init__(self, obs, atoms, fock_builder, charge=0):
+    def __init__(self, obs, atoms, fock_builder, charge=0, stv=None):
+        """stv: (S, T, V) numpy matrices, e.g. from the GPU (capi.onebody); default: the host numpy evaluation
+        (onebody.compute_1body_ints), which the CPU tests use to pin the oracle to the golden energies."""
         self.obs, self.atoms, self.fock_builder = obs, atoms, fock_builder
         nelec = sum(a.atomic_number for a in atoms) - charge
         if nelec % 2:
             raise ValueError("RHF needs an even number of electrons")
         self.ndocc = nelec // 2
         self.enuc = onebody.nuclear_repulsion(atoms)
-        self.S, self.T, self.V = onebody.compute_1body_ints(obs, atoms)
+        self.S, self.T, self.V = stv if stv is not None else onebody.compute_1body_ints(obs, atoms)
         self.H = self.T + self.V
         self.X, self.rank, self.cond = conditioning_orthogonalizer(self.S)
         self.history = []
@@ -234,18 +236,15 @@ class RHFDevice:
 def hf_forces(scf, builder, precision=None, use_schwarz=False):
     """The force block of the reference's driver (tests/hartree-fock/hartree-fock++.cc:596-716) for a
     converged RHF / RHFDevice object: one-body, Pulay, two-body and nuclear-repulsion contributions and their
-    sum, each [natoms, 3].  The two-body part comes from the GPU (FockBuilder.forces_2body =
-    compute_2body_fock_deriv<1> traced with D); the one-body derivative integrals are host numpy
-    (onebody.compute_1body_ints_deriv), like the reference's Engine::compute1 set-up steps."""
+    sum, each [natoms, 3].  One-body and Pulay parts: FockBuilder.forces_1body (lb200_onebody_forces: the
+    derivative integrals of compute_1body_ints_deriv contracted with D and W on the GPU); two-body part:
+    FockBuilder.forces_2body (compute_2body_fock_deriv<1> traced with D on the GPU)."""
     to_np = (lambda x: x.detach().cpu().numpy()) if hasattr(scf.D, "detach") else np.asarray
     D, C, ev = to_np(scf.D), to_np(scf.C), to_np(scf.evals)
-    obs, atoms = scf.obs, scf.atoms
-    na = len(atoms)
-    S1, T1, V1 = onebody.compute_1body_ints_deriv(obs, atoms)
-    F1 = 2.0 * np.einsum("kij,ij->k", T1 + V1, D).reshape(na, 3)                 # :601-612
+    atoms = scf.atoms
     Co = C[:, :scf.ndocc]
     W = (Co * ev[:scf.ndocc]) @ Co.T                                              # :617-619
-    FP = -2.0 * np.einsum("kij,ij->k", S1, W).reshape(na, 3)                      # :620-627
+    F1, FP = builder.forces_1body(D, W, atoms)                                    # :601-627
     if precision is None:
         precision = np.finfo(float).eps      # compute_2body_fock_deriv's default, hartree-fock++.cc:158-162
     # the reference calls compute_2body_fock_deriv<1>(obs, atoms, D) without a Schwarz matrix (:649): no screening

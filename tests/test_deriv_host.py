@@ -163,3 +163,73 @@ def test_gradient_oracle_matches_finite_difference_of_fock_energy(oracle):
         cm[a, x] -= h
         fd = (energy(cp) - energy(cm)) / (2 * h)
         assert abs(fd - g[a, x]) <= 1e-6 * max(1.0, np.abs(g).max()), (a, x, fd, g[a, x])
+
+
+# ---------------------------------------------------------------------------------------------------
+# one-body forces: the __host__ __device__ core of lb200_onebody_forces compiled for the CPU
+# ---------------------------------------------------------------------------------------------------
+def onebody_force_inputs(bs, atoms, seed=7):
+    """random symmetric D, W in the basis functions of `bs`, their Cartesian-ised twins C^T D C, and the
+    reference values from the numpy derivative integrals (pinned to the reference's golden forces in test_scf.py)"""
+    from libint_b200 import onebody
+    rng = np.random.default_rng(seed)
+    n = bs.nbf
+    D = rng.standard_normal((n, n)) * 0.3
+    D = 0.5 * (D + D.T)
+    W = rng.standard_normal((n, n)) * 0.3
+    W = 0.5 * (W + W.T)
+    S1, T1, V1 = onebody.compute_1body_ints_deriv(bs, atoms)
+    F1 = 2.0 * np.einsum("kij,ij->k", T1 + V1, D)
+    FP = -2.0 * np.einsum("kij,ij->k", S1, W)
+    nbfc = sum(nc(s.l) for s in bs)
+    C = np.zeros((n, nbfc))            # pure (or Cartesian) function <- Cartesian components, block diagonal
+    oc = 0
+    for i, s in enumerate(bs):
+        k = nc(s.l)
+        blk = onebody.cart_to_pure(s.l) if s.pure else np.eye(k)
+        C[bs.shell2bf[i]:bs.shell2bf[i] + blk.shape[0], oc:oc + k] = blk
+        oc += k
+    return D, W, C.T @ D @ C, C.T @ W @ C, F1, FP
+
+
+def host_onebody_forces(tmp_path_factory_dir, bs, atoms, Dc, Wc):
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(str(tmp_path_factory_dir), "libob1host.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-I", os.path.join(root, "libint_b200", "csrc"),
+                               os.path.join(root, "tests", "cxx", "onebody_forces_host.cc"), "-o", so])
+    lib = ctypes.CDLL(so)
+    l, pure, nprim, O, alpha, coeff = bs.flat()
+    off = np.concatenate([[0], np.cumsum(nprim)]).astype(np.int32)
+    s2c = np.concatenate([[0], np.cumsum([nc(int(x)) for x in l])]).astype(np.int32)
+    s2a = np.ascontiguousarray(bs.shell2atom, dtype=np.int32)
+    ch = np.ascontiguousarray([[a.atomic_number, *a.xyz] for a in atoms], dtype=np.float64)
+    F = np.zeros((2, 3 * len(atoms)))
+    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    arrs = [np.ascontiguousarray(x) for x in (l, nprim, off, O, alpha, coeff, s2c, s2a, ch, Dc, Wc)]
+    ptr = [x.ctypes.data_as(ip if x.dtype == np.int32 else dp) for x in arrs]
+    lib.ob1_host_forces(ctypes.c_int(len(l)), ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], ptr[6], ptr[7],
+                        ctypes.c_int(len(atoms)), ptr[8], ptr[9], ptr[10], ctypes.c_int(Dc.shape[0]),
+                        F.ctypes.data_as(dp))
+    return F[0], F[1]
+
+
+@pytest.mark.parametrize("name,geom,set_pure", [("aug-cc-pvdz", "h2o_rotated", None), ("6-31g*", "h2o", None),
+                                                ("def2-tzvp", "h2o_rotated", None), ("cc-pvdz", "h2o", False)])
+def test_onebody_force_kernel_core_on_the_cpu(tmp_path, name, geom, set_pure):
+    """lb200_onebody_forces' per-shell-pair routine (onebody_deriv.cuh, compiled by g++ here) against
+    2 sum (T1 + V1) o D and -2 sum S1 o W from the numpy derivative integrals: pure d / f, Cartesian d,
+    diffuse functions, three centres."""
+    from libint_b200.basis import BasisSet, H2O_ROTATED_XYZ_ANGSTROM, H2O_XYZ_ANGSTROM, atoms_from_tuples
+    atoms = atoms_from_tuples(H2O_ROTATED_XYZ_ANGSTROM if geom == "h2o_rotated" else H2O_XYZ_ANGSTROM)
+    bs = BasisSet(name, atoms)
+    if set_pure is not None:
+        bs.set_pure(set_pure)
+    D, W, Dc, Wc, F1, FP = onebody_force_inputs(bs, atoms)
+    g1, gp = host_onebody_forces(tmp_path, bs, atoms, Dc, Wc)
+    np.testing.assert_allclose(g1, F1, rtol=1e-11, atol=1e-11 * np.abs(F1).max())
+    np.testing.assert_allclose(gp, FP, rtol=1e-11, atol=1e-11 * np.abs(FP).max())

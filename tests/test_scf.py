@@ -251,8 +251,9 @@ def _cxx_driver_inputs(tmp_path):
 @pytest.mark.gpu
 def test_cxx_driver_reproduces_the_reference_goldens(tmp_path):
     """hartree-fock-b200 (C++ host program on the C ABI, no Python in the loop): the reference's golden SCF
-    energies and, for its validation run, the golden two-body and nuclear-repulsion forces
-    (hartree-fock-validate.py:14, hartree-fock++-validate.py:49,97-107), parsed with the validators' patterns."""
+    energies and, for its validation run, all five golden force vectors -- one-body and Pulay (lb200_onebody_forces),
+    two-body (lb200_fock_grad), nuclear repulsion and their sum (hartree-fock-validate.py:14,
+    hartree-fock++-validate.py:49,84-112) -- parsed with the validators' patterns and checked to their tolerances."""
     import os
     import re
     import subprocess
@@ -268,8 +269,7 @@ def test_cxx_driver_reproduces_the_reference_goldens(tmp_path):
         m = [x for x in m if x]
         assert len(m) == 1 and abs(float(m[0].group(1)) - eref) < tol, r.stdout[-600:]
         if forces:
-            for key in ("2-body", "nuclear repulsion"):
-                ref, ftol = REF_FORCES[key]
+            for key, (ref, ftol) in REF_FORCES.items():   # 1-body, Pulay, 2-body, nuclear repulsion, Hartree-Fock
                 mm = [re.match(r"\*\* %s forces =" % re.escape(key) + num * 9, ln) for ln in r.stdout.splitlines()]
                 mm = [x for x in mm if x]
                 assert len(mm) == 1, key
@@ -345,6 +345,42 @@ def test_onebody_device_matches_host(ctx):
         np.testing.assert_allclose(S, Sh, rtol=1e-12, atol=1e-13, err_msg=name)
         np.testing.assert_allclose(T, Th, rtol=1e-12, atol=1e-12, err_msg=name)
         np.testing.assert_allclose(V, Vh, rtol=1e-12, atol=1e-12, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_onebody_forces_device_matches_host(ctx):
+    """lb200_onebody_forces (one-body and Pulay force sums on the GPU, hartree-fock++.cc:601-627) against the numpy
+    derivative integrals contracted with the same random symmetric D and W: pure d / f, Cartesian d, diffuse
+    functions; host and device (torch) inputs; argument errors."""
+    import torch
+    from libint_b200 import capi
+    from libint_b200.basis import BasisSet
+    from test_deriv_host import onebody_force_inputs
+    for name, geom, pure in (("aug-cc-pvdz", "h2o_rotated", None), ("6-31g*", "h2o", None),
+                             ("def2-tzvp", "h2o_rotated", None), ("cc-pvdz", "h2o", False)):
+        atoms = _atoms(geom)
+        bs = BasisSet(name, atoms)
+        if pure is not None:
+            bs.set_pure(pure)
+        D, W, _, _, F1, FP = onebody_force_inputs(bs, atoms)
+        B = capi.Basis(ctx, *bs.flat())
+        charges = [(float(a.atomic_number), a.xyz) for a in atoms]
+        g1, gp = capi.onebody_forces(ctx, B, charges, bs.shell2atom, D, W)
+        np.testing.assert_allclose(g1.ravel(), F1, rtol=1e-11, atol=1e-11 * np.abs(F1).max(), err_msg=name)
+        np.testing.assert_allclose(gp.ravel(), FP, rtol=1e-11, atol=1e-11 * np.abs(FP).max(), err_msg=name)
+        dev = torch.device("cuda", ctx.device)
+        Dt, Wt = torch.as_tensor(D, device=dev), torch.as_tensor(W, device=dev)
+        torch.cuda.synchronize(dev)
+        h1, hp = capi.onebody_forces(ctx, B, charges, bs.shell2atom, Dt, Wt)
+        np.testing.assert_allclose(h1, g1, rtol=1e-12, atol=1e-12 * np.abs(F1).max(), err_msg=name)
+        np.testing.assert_allclose(hp, gp, rtol=1e-12, atol=1e-12 * np.abs(FP).max(), err_msg=name)
+        # translational invariance of the one-body energy terms: the forces sum to zero over the atoms
+        assert np.abs(g1.sum(axis=0)).max() < 1e-10 * np.abs(F1).max()
+        assert np.abs(gp.sum(axis=0)).max() < 1e-10 * np.abs(FP).max()
+        with pytest.raises(capi.Lb200Error):
+            capi.onebody_forces(ctx, B, charges, [len(atoms)] * B.nshell, D, W)   # shell2atom out of range
+        with pytest.raises(ValueError):
+            capi.onebody_forces(ctx, B, charges, bs.shell2atom[:-1], D, W)
 
 
 @pytest.mark.gpu
