@@ -445,8 +445,27 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
     // without the two index divisions per element.  Measured per 2^20 quartets (profiles/r03_variants.txt):
     // (ds|dd) 0.881 -> 0.801 ms, (ds|dp) 0.529 -> 0.515, (ds|ds) 0.393 -> 0.380; with (p s| rows (three row lanes
     // per quartet, eight quartets per warp) the dense rows collide in the banks: (ps|dd) 0.391 -> 0.418 -- padded.
-    constexpr bool FINPACK = LB200_X_FINPACK && LB == 0 && !TR && !FOCK && K::NAB >= 6;
+#ifndef LB200_X_FINPACK_MINAB_TMA
+#define LB200_X_FINPACK_MINAB_TMA 3
+#endif
+#ifndef LB200_X_TMASTORE
+#define LB200_X_TMASTORE 1
+#endif
+    // Dense rows also for the (p s| rows when (and only when) the block can leave by TMA (LB200_X_FINPACK_MINAB_TMA = 3;
+    // 6 = off).  Measured per 2^20 quartets on one B200 (profiles/r04_variants_tmastore.txt), lane copy-out -> TMA:
+    // (ds|dd) 0.805 -> 0.721 ms, (ds|dp) 0.517 -> 0.468, (ds|ds) 0.381 -> 0.353; padded rows + lane copy-out ->
+    // dense rows + TMA: (ps|dd) 0.394 -> 0.342, (ps|dp) 0.248 -> 0.232, (ps|ds) 0.162 -> 0.160.  One issuing lane per
+    // group instead of one per quartet (LB200_X_TMASTORE = 2): 0.731 / 0.480 / 0.371 for the (ds| classes -- slower.
+    constexpr bool TMA_SHAPE = LB200_X_TMASTORE && (K::NAB * K::NCD) % 2 == 0 && QSIZE % 2 == 0 && K::OFF_FIN % 2 == 0;
+    constexpr bool FINPACK = LB200_X_FINPACK && LB == 0 && !TR && !FOCK &&
+                             (K::NAB >= 6 || (TMA_SHAPE && K::NAB >= LB200_X_FINPACK_MINAB_TMA));
     constexpr int FCS = FINPACK ? K::NCD : K::CS;
+    // LB200_X_TMASTORE: the dense block of a FINPACK class leaves through one TMA bulk copy per quartet
+    // (cp.async.bulk shared -> global, issued by the quartet's row-0 lane) instead of the lanes' LDS + STG loop;
+    // it drains while the Boys lanes evaluate F_m of the next round.  Needs 16-byte aligned source / destination /
+    // size: the block is an even number of doubles, the stage offsets are even, the output pointer is checked.
+    constexpr bool TMASTORE = FINPACK && TMA_SHAPE;
+    const bool tma_out = TMASTORE && (reinterpret_cast<size_t>(p.out) & 15) == 0;
     if constexpr (LB > 0) {
       if (valid && rmeta.row >= K::ROW0)
         static_for<K::NCD>([&](auto ic) {
@@ -457,6 +476,9 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
         static_for<K::NCD>([&](auto ic) {
           Q[K::OFF_FIN + (rmeta.row - K::ROW0) * FCS + decltype(ic)::value] = H[decltype(ic)::value];
         });
+    }
+    if constexpr (TMASTORE) {
+      if (tma_out) bulk_store_fence();   // this lane's part of the final block -> visible to the async proxy
     }
     cp_async_wait_all();   // own copies of the next round's records have landed ...
     sync();                // ... and everybody else's; transposed rows visible
@@ -513,7 +535,21 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       double* __restrict__ o = p.out + (size_t)base * BLK;
       if constexpr (!TR) {
         if constexpr (LB == 0) {
+          if constexpr (TMASTORE) {
+            if (tma_out) {
+              if constexpr (LB200_X_TMASTORE == 2) {   // one lane of the group issues every quartet's copy
+                if (gl == 0)
+                  for (int q2 = 0; q2 < nvalid; ++q2)
+                    bulk_store(o + (size_t)q2 * BLK, smem + (size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN,
+                               (unsigned)(BLK * sizeof(double)));
+              } else {
+                if (valid && rmeta.row == 0)
+                  bulk_store(p.out + (size_t)task * BLK, Q + K::OFF_FIN, (unsigned)(BLK * sizeof(double)));
+              }
+            }
+          }
           if constexpr (FINPACK) {
+            if (!tma_out)
             for (int q2 = 0; q2 < nvalid; ++q2) {
               const double* __restrict__ src = smem + (size_t)(g * QPG + q2) * QSIZE + K::OFF_FIN;
               double* __restrict__ dst = o + (size_t)q2 * BLK;
@@ -542,6 +578,10 @@ eri_rowreg_prim_kernel(const EriParams p, const RowInfo* __restrict__ rows) {
       // every finite table entry
       if (touched != touched) b2.pfac = touched;
       if constexpr (!LB200_DIAG_NOBOYS) boys_finish(b2, SN);
+    }
+    if constexpr (TMASTORE) {
+      // the bulk copy has read its block: the next round's cross terms may overwrite it after the top barrier
+      if (tma_out && (LB200_X_TMASTORE == 2 ? gl == 0 : (valid && rmeta.row == 0))) bulk_store_wait_read();
     }
     ocur = onext;
     deg_cur = tk_next.deg;
