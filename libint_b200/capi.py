@@ -442,6 +442,10 @@ def onebody_forces(ctx, basis, charges, shell2atom, D, W):
         W = np.ascontiguousarray(W, dtype=np.float64)
         pD, pW, on_dev = vp(D.ctypes.data), vp(W.ctypes.data), 0
     else:
+        import torch
+        for M in (D, W):
+            if M.dtype != torch.float64 or not M.is_cuda or M.device.index != ctx.device:
+                raise ValueError("onebody_forces: device inputs must be float64 CUDA tensors on the context's GPU")
         D, W = D.contiguous(), W.contiguous()
         pD, pW, on_dev = vp(D.data_ptr()), vp(W.data_ptr()), 1
     if tuple(D.shape) != (n, n) or tuple(W.shape) != (n, n):
