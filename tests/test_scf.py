@@ -105,6 +105,21 @@ def test_onebody_invariants():
     np.testing.assert_allclose(ev[0], ev[1], rtol=0, atol=2e-6)  # rotated file has 16 digits of a 5-digit geometry
 
 
+def test_cartesian_standard_normalization_known_answers():
+    """tests/unit/test-core.cc:80-135 ("cartesian uniform normalization", the standard-convention half): the
+    self-overlap of a Cartesian d / f shell Shell{{1.0}, {{l, false, {1.0}}}, {0, 0, 0}} has the diagonal
+    1, 1/3, 1/3, 1, 1/3, 1 (check_std_2) and 1, 1/5, 1/5, 1/5, 1/15, 1/5, 1, 1/5, 1/5, 1 (check_std_3): every
+    component carries the normalization of x^l.  Pins the host one-body evaluation (the checker of the GPU
+    one-body kernels) and the two-electron convention it shares to the reference's own known answers."""
+    from libint_b200 import onebody
+    from libint_b200.basis import BasisSet, Shell
+    want = {2: [1, 1 / 3, 1 / 3, 1, 1 / 3, 1], 3: [1, 1 / 5, 1 / 5, 1 / 5, 1 / 15, 1 / 5, 1, 1 / 5, 1 / 5, 1]}
+    for l, diag in want.items():
+        bs = BasisSet(shells=[Shell(l, [(1.0, 1.0)], pure=False)])
+        S, _, _ = onebody.compute_1body_ints(bs, [])
+        np.testing.assert_allclose(np.diag(S), diag, rtol=1e-13, atol=0)
+
+
 def test_boys_host():
     from libint_b200.onebody import boys
     from scipy.special import hyp1f1
