@@ -120,6 +120,32 @@ def test_cartesian_standard_normalization_known_answers():
         np.testing.assert_allclose(np.diag(S), diag, rtol=1e-13, atol=0)
 
 
+def test_nuclear_attraction_golden_vectors_of_the_reference():
+    """tests/unit/test-1body.cc:45-110 ("electrostatic potential"): Engine(Operator::nuclear) shell sets of two
+    contracted pure d shells in the field of the DefaultFixture's four point charges (fixture.h:38-41), printed there
+    to 16 digits in standard solid-harmonic order -- (0|V|0) (the reference prescales by 2.3 and divides it out) and (0|V|1).  Pins the host one-body
+    evaluation, i.e. the checker of lb200_onebody / lb200_onebody_forces (the GPU half compares against it)."""
+    from libint_b200 import onebody
+    from libint_b200.basis import Atom, BasisSet, Shell
+    atoms = [Atom(8, 0., 0., 0.), Atom(8, 0., 0., 2.), Atom(1, 0., -1., -1.), Atom(1, 0., 1., 3.)]
+    bs = BasisSet(shells=[Shell(2, [(1.0, 1.0), (3.0, 0.3)], origin=(0., 0., 0.), pure=True),
+                          Shell(2, [(2.0, 1.0), (5.0, 0.2)], origin=(1., 1., 1.), pure=True)])
+    _, _, V = onebody.compute_1body_ints(bs, atoms)
+    ref00 = [-1.238239259091998e+01, 0, 0, -5.775996163160049e-02, 0, 0, -1.301230978657952e+01,
+             -6.796143730068988e-02, 0, 1.139389632827834e-01, 0, -6.796143730068988e-02, -1.343732979153083e+01, 0,
+             -1.478824785355970e-02, -5.775996163160049e-02, 0, 0, -1.284475452992947e+01, 0, 0,
+             1.139389632827834e-01, -1.478824785355970e-02, 0, -1.241040347301479e+01]
+    ref01 = [-4.769186621041819e-01, -9.303619356400431e-01, -1.559058302243514e+00, -9.290824121864600e-01,
+             -5.835786921473129e-04, -1.159266418436018e+00, -3.770080831197964e-01, 9.572841308198474e-01,
+             -8.291498398421207e-01, -1.663667687168316e+00, -2.171951144148577e+00, 1.074249956874296e+00,
+             2.128355904665372e+00, 1.074590109905394e+00, -3.485163651594458e-03, -1.160865205880651e+00,
+             -8.344173649626901e-01, 9.566621490332916e-01, -3.760919234260182e-01, 1.660514988916377e+00,
+             -1.120272634615116e-03, -1.385603731947886e+00, -2.105750177166632e-03, 1.380654897976564e+00,
+             2.115041199099945e+00]
+    np.testing.assert_allclose(V[0:5, 0:5].ravel(), ref00, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(V[0:5, 5:10].ravel(), ref01, rtol=1e-13, atol=1e-13)
+
+
 def test_boys_host():
     from libint_b200.onebody import boys
     from scipy.special import hyp1f1
