@@ -87,6 +87,17 @@ def test_basisset_matches_reference_reader(oracle):
             np.testing.assert_array_equal(x, y)
 
 
+def test_basis_cartesian_vs_solid_defaults_known_answer():
+    """tests/unit/test-basis.cc:24-49: O2 in 6-31G* has Cartesian d shells, 2 * (1*3 + 3*2 + 6*1) = 30 functions
+    (basis.h.in:368-386); the correlation-consistent and def2 sets use solid harmonics for l >= 2."""
+    from libint_b200.basis import Atom, BasisSet, ANGSTROM_TO_BOHR
+    o2 = [Atom(8, 0., 0., 0.), Atom(8, 0., 0., 1.5 * ANGSTROM_TO_BOHR)]
+    assert BasisSet("6-31g*", o2).nbf == 30
+    assert BasisSet("6-31g", o2).nbf == 18
+    assert BasisSet("cc-pvdz", o2).nbf == 2 * (3 + 3 * 2 + 5)
+    assert all(s.pure == (s.l > 1) for s in BasisSet("def2-tzvp", o2))
+
+
 def test_read_dotxyz(tmp_path):
     from libint_b200.basis import ANGSTROM_TO_BOHR, read_dotxyz
     p = tmp_path / "h2o.xyz"
