@@ -102,7 +102,7 @@ def build_driver(force=False):
     (csrc/tools/hartree_fock_b200.cc above include/libint_b200.hpp; plain g++, no CUDA headers)."""
     src = os.path.join(CSRC, "tools", "hartree_fock_b200.cc")
     inc = os.path.join(HERE, "..", "include")
-    deps = [os.path.join(inc, "libint_b200.h"), os.path.join(inc, "libint_b200.hpp")]
+    deps = [os.path.join(inc, "libint_b200.h"), os.path.join(inc, "libint_b200.hpp"), os.path.join(inc, "libint_b200_basis.hpp")]
     if force or _newer(src, DRIVER, deps):
         _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-I", inc, src, "-o", DRIVER, "-L", OUT,
               "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])

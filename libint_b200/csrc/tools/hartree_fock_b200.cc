@@ -24,124 +24,13 @@
 #include <map>
 #include <sstream>
 
-#include "libint_b200.hpp"
+#include "libint_b200_basis.hpp"
 
 namespace {
 
 using Matrix = std::vector<double>;   // row-major n x n (or n x m where noted)
-struct Atom { int Z; double x, y, z; };
-
-// ---- minimal JSON reader for the packed basis files: {"name": ..., "shells": {"Z": [[l, [exps], [coefs]], ...]}}
-struct Json {
-  const std::string& s;
-  size_t i = 0;
-  explicit Json(const std::string& text) : s(text) {}
-  void ws() { while (i < s.size() && std::isspace((unsigned char)s[i])) ++i; }
-  bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { ++i; return true; } return false; }
-  void expect(char c) { if (!eat(c)) throw std::runtime_error(std::string("basis file: expected '") + c + "'"); }
-  std::string str() {
-    expect('"');
-    std::string r;
-    while (i < s.size() && s[i] != '"') r += s[i++];
-    ++i;
-    return r;
-  }
-  double num() {
-    ws();
-    char* end = nullptr;
-    const double v = std::strtod(s.c_str() + i, &end);
-    if (end == s.c_str() + i) throw std::runtime_error("basis file: number expected");
-    i = end - s.c_str();
-    return v;
-  }
-  std::vector<double> numlist() {
-    std::vector<double> v;
-    expect('[');
-    if (eat(']')) return v;
-    do v.push_back(num()); while (eat(','));
-    expect(']');
-    return v;
-  }
-};
-struct RawShell { int l; std::vector<double> exps, coefs; };
-
-std::map<int, std::vector<RawShell>> read_basis(const std::string& path, std::string& name) {
-  std::ifstream is(path);
-  if (!is) throw std::runtime_error("cannot open basis file " + path);
-  std::stringstream ss;
-  ss << is.rdbuf();
-  const std::string text = ss.str();
-  Json j(text);
-  std::map<int, std::vector<RawShell>> out;
-  j.expect('{');
-  do {
-    const std::string key = j.str();
-    j.expect(':');
-    if (key == "name") {
-      name = j.str();
-    } else if (key == "shells") {
-      j.expect('{');
-      do {
-        const int Z = std::atoi(j.str().c_str());
-        j.expect(':');
-        j.expect('[');
-        do {
-          RawShell sh;
-          j.expect('[');
-          sh.l = (int)j.num();
-          j.expect(',');
-          sh.exps = j.numlist();
-          j.expect(',');
-          sh.coefs = j.numlist();
-          j.expect(']');
-          out[Z].push_back(sh);
-        } while (j.eat(','));
-        j.expect(']');
-      } while (j.eat(','));
-      j.expect('}');
-    } else {
-      throw std::runtime_error("basis file: unknown key " + key);
-    }
-  } while (j.eat(','));
-  return out;
-}
-
-// basis.h.in:368-386: the 3-21G / 4-31G / 6-31G families use Cartesian d shells
-bool gaussian_cartesian_d_convention(std::string n) {
-  for (auto& c : n) c = (char)std::tolower((unsigned char)c);
-  if (n.rfind("3-21", 0) == 0 || n.rfind("4-31g", 0) == 0) return true;
-  if (n.rfind("6-31", 0) == 0 && n.size() > 4 && n[4] != '1') {
-    const size_t g = n.find('g');
-    if (g == std::string::npos) return false;
-    if (g + 1 == n.size()) return true;
-    if (n[g + 1] == '*' || n[g + 1] == 's') return true;
-  }
-  return false;
-}
-
-std::vector<Atom> read_dotxyz(const std::string& path, double bohr_to_angstrom) {
-  static const char* sym[] = {"x", "h", "he", "li", "be", "b", "c", "n", "o", "f", "ne"};
-  std::ifstream is(path);
-  if (!is) throw std::runtime_error("cannot open geometry file " + path);
-  std::string line;
-  std::getline(is, line);
-  const int natom = std::atoi(line.c_str());
-  std::getline(is, line);   // comment
-  std::vector<Atom> atoms;
-  for (int a = 0; a < natom; ++a) {
-    std::string el;
-    Atom at{};
-    is >> el >> at.x >> at.y >> at.z;
-    for (auto& c : el) c = (char)std::tolower((unsigned char)c);
-    at.Z = -1;
-    for (int z = 1; z <= 10; ++z)
-      if (el == sym[z]) at.Z = z;
-    if (!is || at.Z < 0) throw std::runtime_error("read_dotxyz: bad atom line / element \"" + el + "\"");
-    at.x /= bohr_to_angstrom; at.y /= bohr_to_angstrom; at.z /= bohr_to_angstrom;
-    atoms.push_back(at);
-  }
-  return atoms;
-}
+using libint_b200::Atom;       // libint2::Atom, read_dotxyz, BasisSet: include/libint_b200_basis.hpp
+using libint_b200::BasisSet;
 
 // ---- small dense linear algebra -------------------------------------------------------------------------------
 Matrix matmul(const Matrix& A, const Matrix& B, int n, int k, int m, bool tA = false, bool tB = false) {
@@ -276,29 +165,13 @@ int main(int argc, char** argv) {
     }
     if (basis_files.empty()) throw std::runtime_error("no basis file given");
     const double b2a = codata2010 ? 0.52917721092 /* atom.h:63, hartree-fock.cc:306 */ : 0.529177210903 /* atom.h:53 */;
-    const std::vector<Atom> atoms = read_dotxyz(argv[1], b2a);
-    std::string bname;
-    std::vector<std::map<int, std::vector<RawShell>>> comps;
-    for (const std::string& f : basis_files) {
-      std::string nm;
-      comps.push_back(read_basis(f, nm));
-      if (bname.empty()) bname = nm;
-    }
-    const bool cart_d = gaussian_cartesian_d_convention(bname);
-    // BasisSet(name, atoms): the element's shells moved to every atom (basis.h.in:99-148)
-    std::vector<libint_b200::Shell> obs;
+    std::ifstream xyz(argv[1]);
+    if (!xyz) throw std::runtime_error(std::string("cannot open geometry file ") + argv[1]);
+    const std::vector<Atom> atoms = libint_b200::read_dotxyz(xyz, b2a);
+    // BasisSet(name, atoms) from explicit component files (basis.h.in:134-180); a missing element is an error here
+    const BasisSet obs = BasisSet::from_files(basis_files, atoms, /*throw_if_no_match=*/true);
     std::vector<int> shell2atom;
-    for (size_t a = 0; a < atoms.size(); ++a) {
-      for (const auto& lib : comps) {
-        const auto it = lib.find(atoms[a].Z);
-        if (it == lib.end()) throw std::runtime_error("basis " + bname + " lacks element Z=" + std::to_string(atoms[a].Z));
-        for (const RawShell& r : it->second) {
-          obs.emplace_back(r.exps, r.l, cart_d ? r.l > 2 : r.l > 1, r.coefs,
-                           std::array<double, 3>{{atoms[a].x, atoms[a].y, atoms[a].z}});
-          shell2atom.push_back((int)a);
-        }
-      }
-    }
+    for (long a : obs.shell2atom(atoms)) shell2atom.push_back((int)a);
     if (dump_basis) {   // l pure nprim Ox Oy Oz, then exponents, then normalization-embedded coefficients
       std::printf("%zu\n", obs.size());
       for (size_t i = 0; i < obs.size(); ++i) {
@@ -314,15 +187,15 @@ int main(int argc, char** argv) {
     std::printf("Atomic Cartesian coordinates (a.u.):\n");
     int nelec = 0;
     for (const Atom& a : atoms) {
-      std::printf("%d %.10f %.10f %.10f\n", a.Z, a.x, a.y, a.z);
-      nelec += a.Z;
+      std::printf("%d %.10f %.10f %.10f\n", a.atomic_number, a.x, a.y, a.z);
+      nelec += a.atomic_number;
     }
     if (nelec % 2) throw std::runtime_error("RHF needs an even number of electrons");
     const int ndocc = nelec / 2;
     double enuc = 0.0;   // :245-255
     for (size_t i = 0; i < atoms.size(); ++i)
       for (size_t j = 0; j < i; ++j)
-        enuc += atoms[i].Z * atoms[j].Z / std::sqrt(std::pow(atoms[i].x - atoms[j].x, 2) + std::pow(atoms[i].y - atoms[j].y, 2) +
+        enuc += atoms[i].atomic_number * atoms[j].atomic_number / std::sqrt(std::pow(atoms[i].x - atoms[j].x, 2) + std::pow(atoms[i].y - atoms[j].y, 2) +
                                                     std::pow(atoms[i].z - atoms[j].z, 2));
 
     libint_b200::FockBuilder fb(obs);
@@ -330,7 +203,7 @@ int main(int argc, char** argv) {
     std::printf("orbital basis set rank = %d\n", n);
     std::printf("Nuclear repulsion energy = %.12f\n", enuc);
     std::vector<std::array<double, 4>> charges;
-    for (const Atom& a : atoms) charges.push_back({{(double)a.Z, a.x, a.y, a.z}});
+    for (const Atom& a : atoms) charges.push_back({{(double)a.atomic_number, a.x, a.y, a.z}});
     const auto STV = fb.compute_1body_ints(charges);
     const Matrix& S = STV[0];
     Matrix H((size_t)n * n);
@@ -429,7 +302,7 @@ int main(int argc, char** argv) {
       for (size_t a2 = 0; a2 < a1; ++a2) {
         const double d[3] = {atoms[a1].x - atoms[a2].x, atoms[a1].y - atoms[a2].y, atoms[a1].z - atoms[a2].z};
         const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-        const double f = atoms[a1].Z * atoms[a2].Z / (std::sqrt(r2) * r2);
+        const double f = atoms[a1].atomic_number * atoms[a2].atomic_number / (std::sqrt(r2) * r2);
         for (int k = 0; k < 3; ++k) { FN[3 * a1 + k] -= d[k] * f; FN[3 * a2 + k] += d[k] * f; }
       }
     print_forces("nuclear repulsion", FN);

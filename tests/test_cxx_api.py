@@ -118,3 +118,43 @@ def test_cxx_forces_vs_golden(driver, tmp_path):
     F2 = np.array([float(x) for x in r.stdout.split()]).reshape(3, 3)
     ref = d["631gs_F2"]
     assert np.abs(F2 - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_cxx_basisset_mirror_matches_the_python_mirror(tmp_path):
+    """CPU: include/libint_b200_basis.hpp -- libint_b200::Atom / read_dotxyz / BasisSet(name, atoms), the C++ mirror of
+    libint2::BasisSet (basis.h.in:89-617) -- gives the same shells, maps and counts as libint_b200.basis.BasisSet (which
+    tests/test_host.py checks against the reference's own reader), incl. the Cartesian-d convention of 6-31G*
+    (test-basis.cc:24-49), the aug-cc-pVDZ decomposition, set_pure, and the error contracts."""
+    from libint_b200 import basis as b
+    out = str(tmp_path / "basis_api_driver")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cxx", "basis_api_driver.cc"), "-o", out,
+                    "-L", LIBDIR, "-llibint_b200", "-Wl,-rpath," + LIBDIR], check=True, capture_output=True, text=True)
+    xyz = tmp_path / "h2o.xyz"
+    xyz.write_text("3\n\n" + "".join("%s %.5f %.5f %.5f\n" % ({8: "O", 1: "H"}[Z], *r) for Z, r in b.H2O_XYZ_ANGSTROM))
+    names = ["sto-3g", "6-31g*", "cc-pvdz", "aug-cc-pVDZ", "def2-tzvp", "cc-pvtz"]
+    env = dict(os.environ, LIBINT_B200_DATA_PATH=os.path.join(ROOT, "libint_b200", "data"))
+    r = subprocess.run([out, str(xyz)] + names, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    atoms = b.atoms_from_tuples(b.H2O_XYZ_ANGSTROM)
+    head = lines[0].split()
+    assert head[:6] == ["natoms", "3", "Z", "8", "1", "1"] and float(head[-1]) == atoms[1].x
+    for k, name in enumerate(names):
+        blk = lines[1 + 8 * k: 9 + 8 * k]
+        bs = b.BasisSet(name, atoms)
+        f = blk[0].split()
+        assert f[0] == name and [int(f[2]), int(f[4]), int(f[6]), int(f[8])] == [len(bs), bs.nbf, bs.max_nprim, bs.max_l]
+        assert [int(x) for x in blk[1].split()[1:]] == list(bs.shell2bf)
+        assert [int(x) for x in blk[2].split()[1:]] == list(bs.shell2atom)
+        assert [int(x) for x in blk[3].split()[1:]] == [list(bs.shell2atom).count(a) for a in range(3)]
+        assert [int(x) for x in blk[4].split()[1:]] == [int(s.pure) for s in bs]
+        assert float(blk[5].split()[1]) == pytest.approx(sum(float(np.sum(s.coeff)) for s in bs), rel=1e-14)
+        bs.set_pure(False)
+        assert int(blk[6].split()[-1]) == bs.nbf
+        bs.set_pure(True)
+        assert int(blk[7].split()[-1]) == bs.nbf
+    assert lines[-3:] == ["unknown: ios_base::failure", "quiet omit: 0 shells", "missing: logic_error"]
+    env.pop("LIBINT_B200_DATA_PATH")
+    r = subprocess.run([out, str(xyz), "sto-3g"], capture_output=True, text=True, env=env)
+    assert r.returncode == 4 and "LIBINT_B200_DATA_PATH" in r.stderr
