@@ -104,7 +104,8 @@ def build_driver(force=False):
     inc = os.path.join(HERE, "..", "include")
     deps = [os.path.join(inc, "libint_b200.h"), os.path.join(inc, "libint_b200.hpp"), os.path.join(inc, "libint_b200_basis.hpp")]
     if force or _newer(src, DRIVER, deps):
-        _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-I", inc, src, "-o", DRIVER, "-L", OUT,
+        _run([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-I", inc,
+              '-DLIBINT_B200_DATADIR="%s"' % os.path.join(HERE, "data"), src, "-o", DRIVER, "-L", OUT,
               "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])
     return DRIVER
 

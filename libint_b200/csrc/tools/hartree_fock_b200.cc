@@ -3,6 +3,7 @@
 // of libint2::Shell / Engine / the Fock builder on the C ABI), no torch, no Python:
 //
 //   hartree-fock-b200 geometry.xyz basis.json [more-basis.json ...] [--codata2010] [--dump-basis]
+//   hartree-fock-b200 geometry.xyz basis-name                         (e.g. aug-cc-pVDZ, the reference's default)
 //
 // geometry: XYZ file in Angstrom (libint2::read_dotxyz, atom.h:83-160); basis: packed files under
 // libint_b200/data/basis (the reference's lib/basis/*.g94 re-packed by tools/pack_basis.py); several files are
@@ -152,7 +153,7 @@ struct DIIS {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s geometry.xyz basis.json [more-basis.json ...] [--codata2010]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s geometry.xyz (basis-name | basis.json [more-basis.json ...]) [--codata2010]\n", argv[0]);
     return 2;
   }
   try {
@@ -169,7 +170,11 @@ int main(int argc, char** argv) {
     if (!xyz) throw std::runtime_error(std::string("cannot open geometry file ") + argv[1]);
     const std::vector<Atom> atoms = libint_b200::read_dotxyz(xyz, b2a);
     // BasisSet(name, atoms) from explicit component files (basis.h.in:134-180); a missing element is an error here
-    const BasisSet obs = BasisSet::from_files(basis_files, atoms, /*throw_if_no_match=*/true);
+    // or, like `hartree-fock++ geometry.xyz basis-name` (:236-244), a single basis NAME looked up under
+    // $LIBINT_B200_DATA_PATH/basis (default: the data directory of the tree this driver was built in)
+    const bool by_name = basis_files.size() == 1 && basis_files[0].find(".json") == std::string::npos;
+    const BasisSet obs = by_name ? BasisSet(basis_files[0], atoms, /*throw_if_no_match=*/true)
+                                 : BasisSet::from_files(basis_files, atoms, /*throw_if_no_match=*/true);
     std::vector<int> shell2atom;
     for (long a : obs.shell2atom(atoms)) shell2atom.push_back((int)a);
     if (dump_basis) {   // l pure nprim Ox Oy Oz, then exponents, then normalization-embedded coefficients

@@ -327,8 +327,10 @@ def test_cxx_driver_basis_reader_matches_the_python_mirror(tmp_path):
     exe, data = _cxx_driver_inputs(tmp_path)
     for geom, files, name in [("h2o", ["sto-3g.json"], "sto-3g"), ("h2o", ["6-31gs.json"], "6-31g*"),
                               ("h2o_rotated", ["cc-pvdz.json", "augmentation-cc-pvdz.json"], "aug-cc-pvdz"),
-                              ("h2o", ["def2-tzvp.json"], "def2-tzvp")]:
-        r = subprocess.run([exe, str(tmp_path / (geom + ".xyz"))] + [os.path.join(data, f) for f in files] +
+                              ("h2o", ["def2-tzvp.json"], "def2-tzvp"),
+                              ("h2o_rotated", None, "aug-cc-pVDZ"), ("h2o", None, "6-31G*")]:   # by name, like hartree-fock++
+        r = subprocess.run([exe, str(tmp_path / (geom + ".xyz"))] +
+                           ([os.path.join(data, f) for f in files] if files else [name]) +
                            ["--dump-basis"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         lines = r.stdout.strip().splitlines()
