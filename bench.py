@@ -666,8 +666,23 @@ def run_grad(args, ctx, dev, stream, rank, world, barrier, max_over_ranks):
         t = torch.tensor([nq], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(t)
         nq = float(t.item())
+    # the other GPU half of the force block: one-body + Pulay sums (lb200_onebody_forces, hartree-fock++.cc:601-627);
+    # set-up sized, every rank evaluates all of it; its own guard so that it can never cost the two-body numbers
+    try:
+        Dn = C @ C.T
+        W = (C * rng.uniform(-1.0, -0.1, C.shape[1])) @ C.T   # like C_occ eps_occ C_occ^T
+        fb.forces_1body(Dn, W, atoms)
+        t1 = time.perf_counter()
+        F1, FP = fb.forces_1body(Dn, W, atoms)
+        onebody = {"seconds": time.perf_counter() - t1,   # this rank's own clock: no collective inside the guard
+                   "max_net_force": float(max(np.abs(F1.sum(axis=0)).max(), np.abs(FP.sum(axis=0)).max())),
+                   "checksum": float(np.abs(F1).sum() + np.abs(FP).sum()),
+                   "note": "host D, W in, 2 x 3 natoms sums out (uploads and Cartesian-isation included)"}
+    except Exception as e:
+        onebody = {"error": "%s: %s" % (type(e).__name__, e)}
     return {"workload": "(H2O)_%d / %s two-body forces, Schwarz x density screened at %g"
                         % (nx * ny * nz, args.grad_basis, args.fock_precision),
+            "onebody_forces": onebody,
             "nbf": n, "natoms": len(atoms), "shell_quartets": nq, "seconds": sec,
             "derivative_shell_sets_per_s": 12 * nq / sec, "device_ms_this_rank": st["ms"],
             "launches_this_rank": st["launches"], "n_gpus": world, "scaling": "strong",
